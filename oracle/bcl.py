@@ -1,0 +1,47 @@
+"""Torch-CPU restatement of the bilateral convolution layer - TEST INFRASTRUCTURE ONLY.
+
+Follows reference nets/bilateralNN.py:148-263 (BilateralConvFlex.forward) for batch size 1, which is the
+only batch size the reference supports (bilateralNN.py:162-165).  Written as a pure function of tensors
+so torch autograd yields the oracle gradients (reference row a17: autograd over splat / gather / conv /
+slice).  dtype float64 gives a tight "truth" for tolerance tests; float32 mimics the reference's own
+arithmetic.  Parity status: PINNED against the live reference (tests/golden/bcl_*.npz).
+"""
+import torch
+
+
+def bcl_forward(features, in_bary, in_off, nbrs, convs, *, use_norm=True, do_splat=True,
+                do_slice=False, out_bary=None, out_off=None, slice_bias=None,
+                last_relu=False, use_leaky=True, dtype=None):
+    """features (1,C_in,N) | (1,C_in,H) if not do_splat; in_bary (1,4,N); in_off (1,4,N) int64;
+    nbrs (1,F,H) int64 with -1 = absent; convs = [(W0 (C1,C_in,F,1), b0), (W1 (C2,C1,1,1), b1), ...].
+    Returns (1,C_out,H), or (1,C_out,N_out) when slicing."""
+    dt = dtype or features.dtype
+    feat = features[0].to(dt)                       # (C,N)
+    nb = nbrs[0]                                    # (F,H)
+    H = nb.shape[-1]
+    C = feat.shape[0]
+    if do_splat:                                    # bilateralNN.py:176-191
+        w = in_bary[0].to(dt)                       # (4,N)
+        rows = (in_off[0] + 1).reshape(-1)          # (4N,) r-major then n, +1: row 0 is the sink
+        contrib = (w[:, None, :] * feat[None, :, :]).permute(0, 2, 1).reshape(-1, C)   # (4N,C)
+        S = torch.zeros(H + 1, C, dtype=dt).index_add(0, rows, contrib)
+        if use_norm:                                # bilateralNN.py:193-211
+            W = torch.zeros(H + 1, dtype=dt).index_add(0, rows, w.reshape(-1))
+            S = S * (1.0 / (W + 1e-5))[:, None]
+    else:                                           # bilateralNN.py:215-221
+        S = torch.cat([torch.zeros(1, C, dtype=dt), feat.t()], 0)
+    X = S[nb + 1]                                   # (F,H,C)  bilateralNN.py:240-242
+    W0, b0 = convs[0]
+    y = torch.einsum("fhc,mcf->hm", X, W0[..., 0].to(dt)) + b0.to(dt)   # Conv2d (F,1) :244
+    for li, (Wk, bk) in enumerate(convs[1:]):       # ReLU between convs, :111-115
+        y = torch.relu(y)
+        y = y @ Wk[:, :, 0, 0].to(dt).t() + bk.to(dt)
+    if last_relu:                                   # :121-134
+        y = torch.nn.functional.leaky_relu(y, 0.1) if use_leaky else torch.relu(y)
+    if not do_slice:
+        return y.t()[None]                          # (1,C_out,H) :248-249
+    ob = out_bary[0].to(dt)                         # (4,N_out)  :251-257 (no +1 here)
+    out = (ob[:, :, None] * y[out_off[0]]).sum(0)   # (N_out,C_out)
+    if slice_bias is not None:                      # :260-261
+        out = out + slice_bias.to(dt)
+    return out.t()[None]

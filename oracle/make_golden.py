@@ -1,0 +1,129 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python -m oracle.make_golden
+
+Lattice goldens come from reference GenerateData.__call__ (nets/generate_data.py:117-193) and
+get_keys_and_barycentric (:56-112); BCL goldens from reference BilateralConvFlex (nets/bilateralNN.py)
+forward + autograd backward on CPU.  Small cases are stored in full; full-size clouds are stored as
+per-array SHA-256 digests plus the vertex counts (a checksum of checksums), so the committed fixtures
+stay small while still pinning the 16k / 131k behaviour.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness  # noqa: E402
+from efgh_b200 import synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def lattice_cases():
+    rng = np.random.default_rng(1234)
+    full = synth.synth_scan(7, "os1-64-16k")
+    cases = {
+        "sub2048": (full[:, :2048], synth.SCALE_MAP),
+        "ragged257": (full[:, 5000:5257], synth.SCALE_MAP),
+        "single": (full[:, :1], synth.SCALE_MAP[:2]),
+        "two": (full[:, :2], synth.SCALE_MAP[:3]),
+        # exact ties in el_minus_gr / points on lattice vertices / half-way rounding
+        "ties": (np.concatenate([np.zeros((3, 4), np.float32),
+                                 rng.integers(-6, 7, size=(3, 120)).astype(np.float32),
+                                 (rng.integers(-40, 41, size=(3, 132)) * 0.25).astype(np.float32)], 1),
+                 synth.SCALE_MAP[:3]),
+        "gauss": ((rng.standard_normal((3, 700)) * 8).astype(np.float32), [[1.0, 1], [0.5, 2], [0.25, 1]]),
+        "noblur": (full[:, 100:400], [[1.0, 1], [0.5, -1], [0.25, 1]]),
+        "upscale": (full[:, 300:600], [[0.5, 1], [1.0, 1], [2.0, 1]]),
+        "negquad": (-np.abs(full[:, 600:900]), synth.SCALE_MAP[:2]),
+    }
+    return cases
+
+
+def run_lattice(g, pc, scale_map):
+    gd = g.GenerateData(3, scale_map, "cpu")
+    keys, bary, elmgr = gd.get_keys_and_barycentric(torch.from_numpy(pc.copy()))
+    _, data = gd(torch.from_numpy(pc.copy()))
+    return keys, data
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    t, g, b = ref_harness.load()
+    # ---- lattice, small cases stored in full
+    for name, (pc, smap) in lattice_cases().items():
+        keys, data = run_lattice(g, pc, smap)
+        blob = {"pc": pc, "scale_map": np.asarray(smap, np.float64), "keys0": keys.astype(np.int32)}
+        for li, d in enumerate(data):
+            blob["L%d_bary" % li] = d["pc1_barycentric"].numpy()
+            blob["L%d_elmgr" % li] = d["pc1_el_minus_gr"].numpy()
+            blob["L%d_off" % li] = d["pc1_lattice_offset"].numpy().astype(np.int32)
+            blob["L%d_nbr" % li] = d["pc1_blur_neighbors"].numpy().astype(np.int32)
+            blob["L%d_cnt" % li] = np.int64(d["pc1_hash_cnt"])
+        np.savez_compressed(os.path.join(OUT, "lattice_%s.npz" % name), **blob)
+        print("lattice", name, pc.shape, [d["pc1_hash_cnt"] for d in data])
+    # ---- lattice, full-size clouds as digests (arrays hashed in the reference's dtypes/layouts)
+    dig = {}
+    for sensor, seed in (("os1-64-16k", 0), ("os1-64-16k", 3), ("os1-64-64k", 0), ("os1-64", 0),
+                         ("os1-64", 1), ("hdl-64", 0), ("nusc-32", 0)):
+        pc = synth.synth_scan(seed, sensor)
+        _, data = run_lattice(g, pc, synth.SCALE_MAP)
+        key = "%s/seed%d" % (sensor, seed)
+        dig[key + "/pc"] = digest(pc)
+        dig[key + "/cnt"] = ",".join(str(d["pc1_hash_cnt"]) for d in data)
+        for li, d in enumerate(data):
+            for k in ("pc1_barycentric", "pc1_el_minus_gr", "pc1_lattice_offset", "pc1_blur_neighbors"):
+                dig["%s/L%d/%s" % (key, li, k)] = digest(d[k].numpy())
+        print("digest", key, dig[key + "/cnt"])
+    with open(os.path.join(OUT, "lattice_digests.txt"), "w") as f:
+        for k in sorted(dig):
+            f.write("%s %s\n" % (k, dig[k]))
+    # ---- BCL forward/backward on small lattices
+    torch.manual_seed(0)
+    pc = synth.synth_scan(11, "os1-64-16k")[:, :1500]
+    gd = g.GenerateData(3, [[1.0, 1], [0.5, 1]], "cpu")
+    _, data = gd(torch.from_numpy(pc.copy()))
+    d0, d1 = data
+    N, H = pc.shape[1], d0["pc1_hash_cnt"]
+    for name, kw in {
+        "splat_noslice": dict(num_input=12, num_output=[10, 7], do_splat=True, do_slice=False, use_norm=True, last_relu=False),
+        "splat_slice_bias": dict(num_input=8, num_output=[16, 9], do_splat=True, do_slice=True, use_norm=True, last_relu=True),
+        "nonorm_single": dict(num_input=5, num_output=[6], do_splat=True, do_slice=False, use_norm=False, last_relu=False),
+        "nosplat_three": dict(num_input=6, num_output=[8, 8, 4], do_splat=False, do_slice=True, use_norm=True, last_relu=True),
+        "enet_l0": dict(num_input=36, num_output=[32, 32], do_splat=True, do_slice=False, use_norm=True, last_relu=False),
+    }.items():
+        use_leaky = name != "nosplat_three"
+        m = b.BilateralConvFlex(3, 1, kw["num_input"], kw["num_output"], "cpu", use_bias=True,
+                                use_leaky=use_leaky, use_norm=kw["use_norm"], do_splat=kw["do_splat"],
+                                do_slice=kw["do_slice"], last_relu=kw["last_relu"], chunk_size=-1)
+        for p in m.parameters():
+            torch.nn.init.normal_(p, 0, 0.2)
+        n_in = N if kw["do_splat"] else H
+        feat = torch.randn(1, kw["num_input"], n_in, requires_grad=True)
+        out = m(feat, d0["pc1_barycentric"], d0["pc1_lattice_offset"], d0["pc1_blur_neighbors"],
+                d0["pc1_barycentric"] if kw["do_slice"] else None,
+                d0["pc1_lattice_offset"] if kw["do_slice"] else None)
+        gout = torch.randn_like(out)
+        out.backward(gout)
+        blob = {"pc": pc, "feat": feat.detach().numpy(), "out": out.detach().numpy(), "gout": gout.numpy(),
+                "gfeat": feat.grad.numpy(), "bary": d0["pc1_barycentric"].numpy(),
+                "off": d0["pc1_lattice_offset"].numpy().astype(np.int32),
+                "nbr": d0["pc1_blur_neighbors"].numpy().astype(np.int32),
+                "cfg": np.array([kw["num_input"], int(kw["do_splat"]), int(kw["do_slice"]), int(kw["use_norm"]),
+                                 int(kw["last_relu"]), int(use_leaky)] + kw["num_output"], np.int64)}
+        for k, p in m.named_parameters():
+            blob["p_" + k] = p.detach().numpy()
+            blob["g_" + k] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, "bcl_%s.npz" % name), **blob)
+        print("bcl", name, tuple(out.shape), float(out.abs().mean()))
+
+
+if __name__ == "__main__":
+    main()

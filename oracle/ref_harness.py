@@ -1,0 +1,81 @@
+"""Live-reference harness (TEST INFRASTRUCTURE, this container only).
+
+Imports the UNMODIFIED reference hot-path files from /root/reference by file path:
+nets/transforms.py, nets/generate_data.py, nets/bilateralNN.py, with lib/khash*.h compiled by the
+reference's own cffi build script into oracle/_ref/.  Nothing is copied into the repo; /root/reference
+does not exist on the GPU box, so this module is only used (a) by oracle/make_golden.py to produce
+tests/golden/*.npz and (b) by `-m "not gpu"` tests that are skipped when the reference is absent.
+
+Shims: numba.cffi_support moved to numba.core.typing.cffi_utils; the `nets` package
+__init__ drags in matplotlib/open3d, so a stub package is registered instead.
+"""
+import importlib.util
+import os
+import shutil
+import subprocess
+import sys
+import types
+
+REF_ROOT = os.environ.get("EFGH_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_OUT = os.path.join(HERE, "_ref")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "nets", "generate_data.py"))
+
+
+def build_khash_ffi():
+    """Run the reference's lib/build_khash_cffi.py in oracle/_ref/ (needs a writable cwd)."""
+    os.makedirs(REF_OUT, exist_ok=True)
+    built = [f for f in os.listdir(REF_OUT) if f.startswith("_khash_ffi") and f.endswith(".so")]
+    if built:
+        return
+    tmp = os.path.join(REF_OUT, "_cffi_build")
+    os.makedirs(tmp, exist_ok=True)
+    for f in ("khash.h", "khash_int2int.h", "build_khash_cffi.py"):
+        shutil.copy(os.path.join(REF_ROOT, "lib", f), tmp)
+    subprocess.check_call([sys.executable, "build_khash_cffi.py"], cwd=tmp,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for f in os.listdir(tmp):
+        if f.startswith("_khash_ffi") and f.endswith(".so"):
+            shutil.copy(os.path.join(tmp, f), REF_OUT)
+    shutil.rmtree(tmp)  # reference sources never stay in the repo tree
+
+
+_mods = {}
+
+
+def load():
+    """Returns (transforms, generate_data, bilateralNN) modules of the live reference."""
+    if _mods:
+        return _mods["t"], _mods["g"], _mods["b"]
+    if not available():
+        raise RuntimeError("reference not present at %s" % REF_ROOT)
+    build_khash_ffi()
+    if REF_OUT not in sys.path:
+        sys.path.insert(0, REF_OUT)
+    import numba
+    import numba.core.typing.cffi_utils as cffi_utils
+    if not hasattr(numba, "cffi_support"):
+        numba.cffi_support = cffi_utils
+        sys.modules["numba.cffi_support"] = cffi_utils
+    pkg = types.ModuleType("refnets")
+    pkg.__path__ = [os.path.join(REF_ROOT, "nets")]
+    sys.modules["refnets"] = pkg
+
+    def _imp(name):
+        spec = importlib.util.spec_from_file_location(
+            "refnets." + name, os.path.join(REF_ROOT, "nets", name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["refnets." + name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _mods["t"] = _imp("transforms")
+        _mods["g"] = _imp("generate_data")
+        _mods["b"] = _imp("bilateralNN")
+    return _mods["t"], _mods["g"], _mods["b"]

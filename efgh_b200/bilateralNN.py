@@ -1,0 +1,330 @@
+"""BilateralConvFlex - drop-in for reference nets/bilateralNN.py:55-263 on hand-written CUDA.
+
+Same constructor arguments, same forward signature, same parameter / buffer names
+(`feat_indices`, `out_indices`, `blur_conv.{0,2,..}.{weight,bias}`, `bias`), so reference checkpoints
+load with strict=True (reference main.py:136) and reference nets/enet.py:30-141 can use it unchanged.
+
+What differs underneath: splat is one vector-atomic scatter into a vertex-major
+matrix instead of two sparse COO coalesces of a (4N, C) temporary; the (1, C, F, H) gathered tensor
+is never materialised - neighbour rows are read straight into the convolution's shared-memory tile;
+the density normalisation is folded into that read.  Forward and backward both run through the C ABI
+in include/efgh_b200.h; there is no PyTorch fallback.
+
+Only batch size 1 is meaningful in the reference (bilateralNN.py:162-165: "batch size can only be 1
+for now"; the splat indices carry no batch offset), so B != 1 raises here instead of silently mixing
+the batch entries.
+"""
+import torch
+import torch.nn as nn
+
+from . import _capi
+
+DELETE_TMP_VARIABLES = False
+
+_ACT = {"none": 0, "relu": 1, "leaky": 2}
+
+
+def init_weights(m):
+    """reference nets/bilateralNN.py:42-53"""
+    if isinstance(m, (nn.Conv2d, nn.Linear, nn.ConvTranspose2d)):
+        m.weight.data.normal_(0, 1e-3)
+        if m.bias is not None:
+            m.bias.data.zero_()
+    elif isinstance(m, nn.BatchNorm2d):
+        m.weight.data.fill_(1)
+        m.bias.data.zero_()
+
+
+def _idx_bits(t):
+    if t.dtype == torch.int64:
+        return 64
+    if t.dtype == torch.int32:
+        return 32
+    raise TypeError("lattice indices must be int64 or int32, got %s" % t.dtype)
+
+
+def _rows(t):
+    """(1, R, n) index / weight tensor -> (tensor, leading dimension) with unit stride along n."""
+    t = t[0]
+    if t.shape[-1] > 1 and t.stride(-1) != 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[-1], 1)
+    return t, max(ld, 1)
+
+
+# ---- thin wrappers over the C ABI -----------------------------------------------------------------
+
+def scatter(feat_cn, w, off, row_shift, rows, want_wsum):
+    """feat_cn (C,n) any strides; w (1,4,n); off (1,4,n).  Returns S (rows, C) [, wsum (rows,)]."""
+    C, n = feat_cn.shape
+    S = torch.zeros((rows, C), dtype=torch.float32, device=feat_cn.device)
+    wsum = torch.zeros((rows,), dtype=torch.float32, device=feat_cn.device) if want_wsum else None
+    w2, w_ld = _rows(w)
+    o2, o_ld = _rows(off)
+    _capi.check(_capi.lib().efgh_bcl_scatter(feat_cn.data_ptr(), feat_cn.stride(0), feat_cn.stride(1), C, n, None,
+                                             w2.data_ptr(), w_ld, o2.data_ptr(), _idx_bits(o2), o_ld, row_shift,
+                                             S.data_ptr(), C, _capi.ptr(wsum), _capi.stream_ptr()),
+                "efgh_bcl_scatter")
+    return S, wsum
+
+
+def inv_norm(wsum):
+    inv = torch.empty_like(wsum)
+    _capi.check(_capi.lib().efgh_bcl_inv_norm(wsum.data_ptr(), inv.data_ptr(), wsum.numel(), None, 0,
+                                              _capi.stream_ptr()), "efgh_bcl_inv_norm")
+    return inv
+
+
+def gather(Z, row_scale, w, off, row_shift, bias, n):
+    """Z (rows, C) vertex-major -> (C, n) channel-major (the reference's layout)."""
+    C = Z.shape[1]
+    out = torch.empty((C, n), dtype=torch.float32, device=Z.device)
+    w2, w_ld = _rows(w)
+    o2, o_ld = _rows(off)
+    _capi.check(_capi.lib().efgh_bcl_gather(Z.data_ptr(), Z.stride(0), C, _capi.ptr(row_scale), n, None,
+                                            w2.data_ptr(), w_ld, o2.data_ptr(), _idx_bits(o2), o_ld, row_shift,
+                                            _capi.ptr(bias), out.data_ptr(), out.stride(0), 1, _capi.stream_ptr()),
+                "efgh_bcl_gather")
+    return out
+
+
+def conv(X, row_scale, nbr, Wt, bias, act, h):
+    """X (rows, C); nbr (1,F,h) or None; Wt (F*C, M) -> Y (h, M)."""
+    C = X.shape[1]
+    M = Wt.shape[1]
+    Y = torch.empty((h, M), dtype=torch.float32, device=X.device)
+    if nbr is not None:
+        nb2, nb_ld = _rows(nbr)
+        F, bits, nbp = nb2.shape[0], _idx_bits(nb2), nb2.data_ptr()
+    else:
+        F, bits, nbp, nb_ld = 1, 64, None, 0
+    _capi.check(_capi.lib().efgh_bcl_conv(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F, h,
+                                          None, Wt.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, 0,
+                                          _capi.stream_ptr()), "efgh_bcl_conv")
+    return Y
+
+
+def conv_dgrad(dY, act_out, act, nbr, Wt, C, rows):
+    h, M = dY.shape
+    if nbr is not None:
+        nb2, nb_ld = _rows(nbr)
+        F, bits, nbp = nb2.shape[0], _idx_bits(nb2), nb2.data_ptr()
+        dX = torch.zeros((rows, C), dtype=torch.float32, device=dY.device)
+    else:
+        F, bits, nbp, nb_ld = 1, 64, None, 0
+        dX = torch.empty((rows, C), dtype=torch.float32, device=dY.device)
+    _capi.check(_capi.lib().efgh_bcl_conv_dgrad(dY.data_ptr(), dY.stride(0), _capi.ptr(act_out),
+                                                act_out.stride(0) if act_out is not None else 0, act, M, nbp, bits,
+                                                nb_ld, F, h, None, Wt.data_ptr(), C, dX.data_ptr(), C,
+                                                _capi.stream_ptr()), "efgh_bcl_conv_dgrad")
+    return dX
+
+
+def conv_wgrad(X, row_scale, nbr, dY, act_out, act, want_bias):
+    h, M = dY.shape
+    C = X.shape[1]
+    if nbr is not None:
+        nb2, nb_ld = _rows(nbr)
+        F, bits, nbp = nb2.shape[0], _idx_bits(nb2), nb2.data_ptr()
+    else:
+        F, bits, nbp, nb_ld = 1, 64, None, 0
+    dWt = torch.zeros((F * C, M), dtype=torch.float32, device=dY.device)
+    db = torch.zeros((M,), dtype=torch.float32, device=dY.device) if want_bias else None
+    _capi.check(_capi.lib().efgh_bcl_conv_wgrad(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F,
+                                                h, None, dY.data_ptr(), dY.stride(0), _capi.ptr(act_out),
+                                                act_out.stride(0) if act_out is not None else 0, act, M,
+                                                dWt.data_ptr(), _capi.ptr(db), _capi.stream_ptr()),
+                "efgh_bcl_conv_wgrad")
+    return dWt, db
+
+
+def _wt_first(W):
+    """Conv2d weight (M, C, F, 1) -> (F*C, M) row-major, k = f*C + c."""
+    M, C, F, _ = W.shape
+    return W[:, :, :, 0].permute(2, 1, 0).reshape(F * C, M).contiguous()
+
+
+def _wt_point(W):
+    """Conv2d 1x1 weight (M, C, 1, 1) -> (C, M)."""
+    return W[:, :, 0, 0].t().contiguous()
+
+
+class _BCLFunction(torch.autograd.Function):
+    """splat -> [norm] -> gather-conv -> (ReLU -> 1x1 conv)* -> [act] -> [slice + bias]"""
+
+    @staticmethod
+    def forward(ctx, cfg, features, in_bary, in_off, nbr, out_bary, out_off, slice_bias, *wb):
+        do_splat, do_slice, use_norm, final_act = cfg
+        if features.shape[0] != 1:
+            raise ValueError("BilateralConvFlex: batch size must be 1 (reference bilateralNN.py:162-165)")
+        feat = features[0]
+        if feat.dtype != torch.float32:
+            feat = feat.float()
+        H = nbr.shape[-1]
+        with torch.cuda.device(feat.device):
+            inv = None
+            if do_splat:
+                S, wsum = scatter(feat, in_bary, in_off, 1, H + 1, use_norm)
+                if use_norm:
+                    inv = inv_norm(wsum)
+            else:
+                S = torch.zeros((H + 1, feat.shape[0]), dtype=torch.float32, device=feat.device)
+                S[1:] = feat.t()
+            nconv = len(wb) // 2
+            xs, ys, wts, acts = [], [], [], []
+            X, rs, nb = S, inv, nbr
+            for k in range(nconv):
+                W, b = wb[2 * k], wb[2 * k + 1]
+                Wt = _wt_first(W) if k == 0 else _wt_point(W)
+                act = _ACT["relu"] if k < nconv - 1 else final_act
+                Y = conv(X, rs, nb, Wt, b, act, H)
+                xs.append(X); ys.append(Y); wts.append(Wt); acts.append(act)
+                X, rs, nb = Y, None, None
+            if do_slice:
+                n_out = out_bary.shape[-1]
+                out = gather(X, None, out_bary, out_off, 0, slice_bias, n_out)[None]
+            else:
+                out = X.t()[None]
+        ctx.cfg = cfg
+        ctx.n_in = feat.shape[-1]
+        ctx.acts = acts
+        ctx.has_slice_bias = slice_bias is not None
+        ctx.save_for_backward(in_bary, in_off, nbr, out_bary, out_off, inv, *xs, *ys, *wts)
+        ctx.nconv = nconv
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        do_splat, do_slice, use_norm, final_act = ctx.cfg
+        saved = ctx.saved_tensors
+        in_bary, in_off, nbr, out_bary, out_off, inv = saved[:6]
+        nconv = ctx.nconv
+        xs = saved[6:6 + nconv]
+        ys = saved[6 + nconv:6 + 2 * nconv]
+        wts = saved[6 + 2 * nconv:6 + 3 * nconv]
+        H = nbr.shape[-1]
+        g = gout[0]
+        if g.dtype != torch.float32:
+            g = g.float()
+        grads_wb = [None] * (2 * nconv)
+        d_slice_bias = None
+        with torch.cuda.device(g.device):
+            if do_slice:
+                dY, _ = scatter(g, out_bary, out_off, 0, H, False)         # adjoint of slice
+                if ctx.has_slice_bias and ctx.needs_input_grad[7]:
+                    d_slice_bias = g.sum(dim=1)
+            else:
+                dY = g.t().contiguous()                                    # (H, C_out)
+            for k in range(nconv - 1, -1, -1):
+                act = ctx.acts[k]
+                act_out = ys[k] if act != 0 else None
+                X = xs[k]
+                first = k == 0
+                need_w = ctx.needs_input_grad[8 + 2 * k]
+                need_b = ctx.needs_input_grad[8 + 2 * k + 1]
+                if need_w or need_b:
+                    dWt, db = conv_wgrad(X, inv if first else None, nbr if first else None, dY, act_out, act, need_b)
+                    if need_w:
+                        if first:
+                            F = nbr.shape[1]
+                            C = X.shape[1]
+                            grads_wb[0] = dWt.view(F, C, -1).permute(2, 1, 0).unsqueeze(-1)
+                        else:
+                            grads_wb[2 * k] = dWt.t()[:, :, None, None]
+                    if need_b:
+                        grads_wb[2 * k + 1] = db
+                if first and not ctx.needs_input_grad[1]:
+                    dY = None
+                    break
+                dY = conv_dgrad(dY, act_out, act, nbr if first else None, wts[k], X.shape[1], X.shape[0])
+            dfeat = None
+            if ctx.needs_input_grad[1] and dY is not None:
+                if do_splat:
+                    dfeat = gather(dY, inv, in_bary, in_off, 1, None, ctx.n_in)[None]   # adjoint of splat (+norm)
+                else:
+                    dfeat = dY[1:].t()[None]
+        return (None, dfeat, None, None, None, None, None, d_slice_bias, *grads_wb)
+
+
+class BilateralConvFlex(nn.Module):
+    def __init__(self,
+                 d, neighborhood_size,
+                 num_input, num_output,
+                 DEVICE,
+                 use_bias,
+                 use_leaky,
+                 use_norm,
+                 do_splat,
+                 do_slice,
+                 last_relu,
+                 chunk_size=1024 * 1024 * 25):
+        """Arguments as reference nets/bilateralNN.py:56-80.  `chunk_size` is accepted and ignored: the
+        fused gather-convolution never materialises the (C, F, H) tensor that chunking bounded."""
+        super(BilateralConvFlex, self).__init__()
+        if d != 3:
+            raise NotImplementedError("efgh_b200 implements the d=3 lattice only")
+        self.d = d
+        self.d1 = d + 1
+        self.neighborhood_size = neighborhood_size
+        self.filter_size = self.get_filter_size()
+        self.num_input = num_input
+        self.num_output = num_output
+        self.DEVICE = DEVICE
+        self.use_bias = use_bias
+        self.use_leaky = use_leaky
+        self.do_splat = do_splat
+        self.do_slice = do_slice
+        self.last_relu = last_relu
+        self.use_norm = use_norm
+        self.MAX_SIZE = chunk_size
+
+        num_final_output = num_output[-1]
+        self.register_buffer('feat_indices', torch.arange(num_input, dtype=torch.long))
+        if self.do_slice:
+            self.register_buffer('out_indices', torch.arange(num_final_output, dtype=torch.long))
+
+        # Same module tree as the reference (bilateralNN.py:103-135) so state_dict keys match; the Conv2d
+        # modules only hold the parameters - forward() feeds them to the CUDA kernels.
+        layers = []
+        n_in = num_input
+        for idx, n_out in enumerate(num_output[:-1]):
+            layers.append(nn.Conv2d(n_in, n_out, kernel_size=(self.filter_size, 1) if idx == 0 else (1, 1),
+                                    stride=1, padding=0, bias=True))
+            layers.append(nn.ReLU(inplace=False))
+            n_in = n_out
+        layers.append(nn.Conv2d(n_in, num_final_output,
+                                kernel_size=(self.filter_size, 1) if len(num_output) == 1 else (1, 1),
+                                stride=1, padding=0, bias=True))
+        if self.last_relu:
+            layers.append(nn.LeakyReLU(0.1, inplace=False) if use_leaky else nn.ReLU(inplace=False))
+        self.blur_conv = nn.Sequential(*layers)
+        for m in self.blur_conv.modules():
+            init_weights(m)
+
+        if self.do_slice and self.use_bias:
+            self.register_parameter('bias', nn.Parameter(data=torch.zeros((num_final_output,), dtype=torch.float32),
+                                                         requires_grad=True))
+
+    def get_filter_size(self):
+        return (self.neighborhood_size + 1) ** self.d1 - self.neighborhood_size ** self.d1
+
+    def forward(self, features,
+                in_barycentric, in_lattice_offset,
+                blur_neighbors,
+                out_barycentric, out_lattice_offset):
+        """Shapes as reference nets/bilateralNN.py:152-160.  Returns (1, C_out, N_out) when slicing, else
+        (1, C_out, H) - the latter as a transposed view of the vertex-major result."""
+        if not features.is_cuda:
+            raise _capi.EfghError("BilateralConvFlex runs on CUDA tensors only; there is no CPU path")
+        final_act = 0
+        if self.last_relu:
+            final_act = _ACT["leaky"] if self.use_leaky else _ACT["relu"]
+        cfg = (self.do_splat, self.do_slice, self.use_norm, final_act)
+        wb = []
+        for m in self.blur_conv:
+            if isinstance(m, nn.Conv2d):
+                wb += [m.weight, m.bias]
+        slice_bias = self.bias if (self.do_slice and self.use_bias) else None
+        return _BCLFunction.apply(cfg, features, in_barycentric, in_lattice_offset, blur_neighbors,
+                                  out_barycentric if self.do_slice else None,
+                                  out_lattice_offset if self.do_slice else None, slice_bias, *wb)

@@ -1,0 +1,564 @@
+// Bilateral convolution layer kernels (reference nets/bilateralNN.py:148-263), fp32 CUDA-core path.
+//
+//   k_scatter   splat (:176-191) + density sum (:193-207); adjoint of slice
+//   k_inv_norm  1 / (wsum + 1e-5)  (:210)
+//   k_gather    slice (:251-261); adjoint of splat
+//   k_conv      neighbour gather (:240-242) fused with the (F,1) / (1,1) convolution (:244): the
+//               reference's (1, C, F, H) gathered tensor (218 MB at level 0) is never materialised -
+//               rows of the vertex-major splat matrix go straight from L2 into the shared-memory tile
+//   k_dgrad / k_wgrad   backward of k_conv (reference: autograd over index + cuDNN)
+//
+// Lattice-side matrices are vertex-major (row = vertex, C contiguous floats) so one neighbour is one
+// contiguous 4*C-byte read and a splat contribution is a handful of 16-byte vector reductions.
+#include "common.cuh"
+
+namespace efgh {
+namespace {
+
+constexpr int kTP = 32;  // points per tile in scatter / gather
+
+// ---------------------------------------------------------------------------------------------
+// scatter: S[off[r,n]+shift, :] += w[r,n] * feat[:, n]
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C, int n_host, const int32_t *n_dev,
+          const float *__restrict__ w, int64_t w_ld, const void *__restrict__ off, int64_t off_ld, int shift,
+          float *S, int64_t ldS, float *wsum) {
+  extern __shared__ float smem[];
+  float *tile = smem;                                   // [C][kTP+1]
+  float *s_w = smem + (size_t)C * (kTP + 1);            // [4][kTP]
+  int *s_row = reinterpret_cast<int *>(s_w + 4 * kTP);  // [4][kTP]
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  const int n_tiles = (n + kTP - 1) / kTP;
+  const bool vec = (C % 4 == 0) && (ldS % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n0 = t * kTP;
+    const int np = min(kTP, n - n0);
+    if (sn == 1) {  // channel-major (C,N): coalesce along points
+      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
+        int c = idx / kTP, p = idx % kTP;
+        tile[c * (kTP + 1) + p] = p < np ? __ldg(feat + c * sc + (n0 + p)) : 0.f;
+      }
+    } else {        // point-major: coalesce along channels
+      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
+        int p = idx / C, c = idx % C;
+        tile[c * (kTP + 1) + p] = p < np ? __ldg(feat + c * sc + (int64_t)(n0 + p) * sn) : 0.f;
+      }
+    }
+    for (int idx = threadIdx.x; idx < 4 * kTP; idx += blockDim.x) {
+      int r = idx / kTP, p = idx % kTP;
+      bool ok = p < np;
+      s_w[idx] = ok ? __ldg(w + r * w_ld + n0 + p) : 0.f;
+      s_row[idx] = ok ? load_idx<IdxT>(off, r * off_ld + n0 + p) + shift : -1;
+    }
+    __syncthreads();
+    if (vec) {
+      const int C4 = C / 4;
+      for (int item = threadIdx.x; item < np * 4 * C4; item += blockDim.x) {
+        const int c4 = item % C4, pr = item / C4, r = pr & 3, p = pr >> 2;
+        const int row = s_row[r * kTP + p];
+        if (row < 0) continue;
+        const float wt = s_w[r * kTP + p];
+        float4 v;
+        v.x = tile[(4 * c4 + 0) * (kTP + 1) + p] * wt;
+        v.y = tile[(4 * c4 + 1) * (kTP + 1) + p] * wt;
+        v.z = tile[(4 * c4 + 2) * (kTP + 1) + p] * wt;
+        v.w = tile[(4 * c4 + 3) * (kTP + 1) + p] * wt;
+        atomicAdd(reinterpret_cast<float4 *>(S + (int64_t)row * ldS) + c4, v);
+        if (wsum && c4 == 0) atomicAdd(wsum + row, wt);
+      }
+    } else {
+      for (int item = threadIdx.x; item < np * 4 * C; item += blockDim.x) {
+        const int c = item % C, pr = item / C, r = pr & 3, p = pr >> 2;
+        const int row = s_row[r * kTP + p];
+        if (row < 0) continue;
+        const float wt = s_w[r * kTP + p];
+        atomicAdd(S + (int64_t)row * ldS + c, tile[c * (kTP + 1) + p] * wt);
+        if (wsum && c == 0) atomicAdd(wsum + row, wt);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_inv_norm(const float *__restrict__ wsum, float *__restrict__ inv, int rows_host,
+                           const int32_t *rows_dev, int rows_extra) {
+  const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x)
+    inv[i] = __fdiv_rn(1.0f, __fadd_rn(wsum[i], 1e-5f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather: out[:, n] = sum_r w[r,n] * Z[off[r,n]+shift, :] * scale[row] + bias
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+k_gather(const float *__restrict__ Z, int64_t ldZ, int C, const float *__restrict__ row_scale, int n_host,
+         const int32_t *n_dev, const float *__restrict__ w, int64_t w_ld, const void *__restrict__ off,
+         int64_t off_ld, int shift, const float *__restrict__ bias, float *__restrict__ out, int64_t sc,
+         int64_t sn) {
+  extern __shared__ float smem[];
+  float *tile = smem;                                   // [C][kTP+1]
+  float *s_w = smem + (size_t)C * (kTP + 1);            // [4][kTP]
+  int *s_row = reinterpret_cast<int *>(s_w + 4 * kTP);  // [4][kTP]
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  const int n_tiles = (n + kTP - 1) / kTP;
+  const bool vec = (C % 4 == 0) && (ldZ % 4 == 0) && ((reinterpret_cast<uintptr_t>(Z) & 15) == 0);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n0 = t * kTP;
+    const int np = min(kTP, n - n0);
+    for (int idx = threadIdx.x; idx < 4 * kTP; idx += blockDim.x) {
+      int r = idx / kTP, p = idx % kTP;
+      bool ok = p < np;
+      int row = ok ? load_idx<IdxT>(off, r * off_ld + n0 + p) + shift : -1;
+      float wt = ok ? __ldg(w + r * w_ld + n0 + p) : 0.f;
+      if (row >= 0 && row_scale) wt *= __ldg(row_scale + row);
+      s_w[idx] = wt;
+      s_row[idx] = row;
+    }
+    __syncthreads();
+    if (vec) {
+      const int C4 = C / 4;
+      for (int item = threadIdx.x; item < np * C4; item += blockDim.x) {
+        const int c4 = item % C4, p = item / C4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = s_row[r * kTP + p];
+          if (row < 0) continue;
+          const float wt = s_w[r * kTP + p];
+          const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + (int64_t)row * ldZ) + c4);
+          acc.x = fmaf(wt, z.x, acc.x); acc.y = fmaf(wt, z.y, acc.y);
+          acc.z = fmaf(wt, z.z, acc.z); acc.w = fmaf(wt, z.w, acc.w);
+        }
+        tile[(4 * c4 + 0) * (kTP + 1) + p] = acc.x;
+        tile[(4 * c4 + 1) * (kTP + 1) + p] = acc.y;
+        tile[(4 * c4 + 2) * (kTP + 1) + p] = acc.z;
+        tile[(4 * c4 + 3) * (kTP + 1) + p] = acc.w;
+      }
+    } else {
+      for (int item = threadIdx.x; item < np * C; item += blockDim.x) {
+        const int c = item % C, p = item / C;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = s_row[r * kTP + p];
+          if (row < 0) continue;
+          acc = fmaf(s_w[r * kTP + p], __ldg(Z + (int64_t)row * ldZ + c), acc);
+        }
+        tile[c * (kTP + 1) + p] = acc;
+      }
+    }
+    __syncthreads();
+    if (sn == 1) {
+      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
+        int c = idx / kTP, p = idx % kTP;
+        if (p < np) out[c * sc + n0 + p] = tile[c * (kTP + 1) + p] + (bias ? __ldg(bias + c) : 0.f);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
+        int p = idx / C, c = idx % C;
+        if (p < np) out[c * sc + (int64_t)(n0 + p) * sn] = tile[c * (kTP + 1) + p] + (bias ? __ldg(bias + c) : 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled fp32 GEMM machinery shared by conv / dgrad / wgrad.
+//   block tile BM x BN, K chunk BK = 16, 256 threads, each thread a TM x TN register tile.
+//   As[BK][BM+4], Bs[BK][BN+4] (k-major so the inner product reads are float4 and conflict-free).
+// ---------------------------------------------------------------------------------------------
+constexpr int BK = 16;
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : 0.1f * v;
+  return v;
+}
+__device__ __forceinline__ float act_bwd(float out, int act) {
+  if (act == 1) return out > 0.f ? 1.f : 0.f;
+  if (act == 2) return out > 0.f ? 1.f : 0.1f;
+  return 1.f;
+}
+
+template <int BM, int BN, int TM, int TN>
+struct Tile {
+  static constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == 256, "256 threads");
+  float acc[TM][TN];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  }
+  __device__ __forceinline__ void mma(const float (*As)[BM + 4], const float (*Bs)[BN + 4]) {
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+};
+
+// Y[h, m] = act(bias[m] + sum_k A[h, k] * Wt[k, m]),  A[h, f*C + c] = X[nbr[f,h]+1, c] * scale[row]
+template <typename IdxT, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256)
+k_conv(const float *__restrict__ X, int64_t ldX, int C, const float *__restrict__ row_scale,
+       const void *__restrict__ nbr, int64_t nbr_ld, int F, int h_host, const int32_t *h_dev,
+       const float *__restrict__ Wt, const float *__restrict__ bias, int M, int act, float *__restrict__ Y,
+       int64_t ldY) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  extern __shared__ int s_rows[];  // [F][BM]
+  const int H = h_dev ? min(*h_dev, h_host) : h_host;
+  const int K = F * C;
+  const int m0 = blockIdx.y * BN;
+  const bool vecA = (C % 4 == 0) && (ldX % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const bool vecB = (M % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
+  Tile<BM, BN, TM, TN> T;
+  for (int h0 = blockIdx.x * BM; h0 < H; h0 += gridDim.x * BM) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < F * BM; idx += 256) {
+      int f = idx / BM, hh = idx % BM;
+      int row = -1;
+      if (h0 + hh < H) row = nbr ? load_idx<IdxT>(nbr, f * nbr_ld + h0 + hh) + 1 : h0 + hh;
+      s_rows[idx] = row;
+    }
+    __syncthreads();
+    T.zero();
+    for (int k0 = 0; k0 < K; k0 += BK) {
+      // A chunk: BM rows x 16 k  (4 float4 units per row)
+      if (vecA) {
+        for (int u = threadIdx.x; u < BM * (BK / 4); u += 256) {
+          const int hh = u / (BK / 4), q = u % (BK / 4);
+          const int k = k0 + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < K) {
+            const int f = k / C, c = k - f * C;
+            const int row = s_rows[f * BM + hh];
+            if (row > 0 || (row == 0 && !nbr)) {
+              v = __ldg(reinterpret_cast<const float4 *>(X + (int64_t)row * ldX + c));
+              if (row_scale) { const float sc = __ldg(row_scale + row); v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+            }
+          }
+          As[4 * q + 0][hh] = v.x; As[4 * q + 1][hh] = v.y; As[4 * q + 2][hh] = v.z; As[4 * q + 3][hh] = v.w;
+        }
+      } else {
+        for (int u = threadIdx.x; u < BM * BK; u += 256) {
+          const int hh = u / BK, kk = u % BK;
+          const int k = k0 + kk;
+          float v = 0.f;
+          if (k < K) {
+            const int f = k / C, c = k - f * C;
+            const int row = s_rows[f * BM + hh];
+            if (row > 0 || (row == 0 && !nbr)) {
+              v = __ldg(X + (int64_t)row * ldX + c);
+              if (row_scale) v *= __ldg(row_scale + row);
+            }
+          }
+          As[kk][hh] = v;
+        }
+      }
+      // B chunk: 16 k x BN m
+      if (vecB) {
+        for (int u = threadIdx.x; u < BK * (BN / 4); u += 256) {
+          const int kk = u / (BN / 4), q = u % (BN / 4);
+          const int k = k0 + kk, m = m0 + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < K && m < M) v = __ldg(reinterpret_cast<const float4 *>(Wt + (int64_t)k * M + m));
+          *reinterpret_cast<float4 *>(&Bs[kk][4 * q]) = v;
+        }
+      } else {
+        for (int u = threadIdx.x; u < BK * BN; u += 256) {
+          const int kk = u / BN, mm = u % BN;
+          const int k = k0 + kk, m = m0 + mm;
+          Bs[kk][mm] = (k < K && m < M) ? __ldg(Wt + (int64_t)k * M + m) : 0.f;
+        }
+      }
+      __syncthreads();
+      T.mma(As, Bs);
+      __syncthreads();
+    }
+    const int tx = threadIdx.x % T.TX, ty = threadIdx.x / T.TX;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int h = h0 + ty * TM + i;
+      if (h >= H) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int m = m0 + tx * TN + j;
+        if (m < M) Y[(int64_t)h * ldY + m] = act_fwd(T.acc[i][j] + (bias ? __ldg(bias + m) : 0.f), act);
+      }
+    }
+  }
+}
+
+// dX[nbr[f,h]+1, c] += sum_m dYm[h, m] * Wt[f*C+c, m]     (GEMM (h x M) . (M x F*C), scattered epilogue)
+template <typename IdxT, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256)
+k_dgrad(const float *__restrict__ dY, int64_t ldY, const float *__restrict__ act_out, int64_t ldA, int act, int M,
+        const void *__restrict__ nbr, int64_t nbr_ld, int F, int h_host, const int32_t *h_dev,
+        const float *__restrict__ Wt, int C, float *dX, int64_t ldX) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int H = h_dev ? min(*h_dev, h_host) : h_host;
+  const int J = F * C;
+  const int j0 = blockIdx.y * BN;
+  Tile<BM, BN, TM, TN> T;
+  for (int h0 = blockIdx.x * BM; h0 < H; h0 += gridDim.x * BM) {
+    T.zero();
+    for (int k0 = 0; k0 < M; k0 += BK) {
+      for (int u = threadIdx.x; u < BM * BK; u += 256) {
+        const int hh = u / BK, kk = u % BK;
+        const int h = h0 + hh, m = k0 + kk;
+        float v = 0.f;
+        if (h < H && m < M) {
+          v = __ldg(dY + (int64_t)h * ldY + m);
+          if (act_out) v *= act_bwd(__ldg(act_out + (int64_t)h * ldA + m), act);
+        }
+        As[kk][hh] = v;
+      }
+      for (int u = threadIdx.x; u < BK * BN; u += 256) {
+        const int jj = u / BK, kk = u % BK;
+        const int j = j0 + jj, m = k0 + kk;
+        Bs[kk][jj] = (j < J && m < M) ? __ldg(Wt + (int64_t)j * M + m) : 0.f;
+      }
+      __syncthreads();
+      T.mma(As, Bs);
+      __syncthreads();
+    }
+    const int tx = threadIdx.x % T.TX, ty = threadIdx.x / T.TX;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int h = h0 + ty * TM + i;
+      if (h >= H) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int col = j0 + tx * TN + j;
+        if (col >= J) continue;
+        if (nbr) {
+          const int f = col / C, c = col - f * C;
+          const int row = load_idx<IdxT>(nbr, f * nbr_ld + h) + 1;
+          if (row > 0) atomicAdd(dX + (int64_t)row * ldX + c, T.acc[i][j]);
+        } else {
+          dX[(int64_t)h * ldX + col] = T.acc[i][j];
+        }
+      }
+    }
+  }
+}
+
+// dWt[f*C+c, m] += sum_h A[h, f*C+c] * dYm[h, m];  dbias[m] += sum_h dYm[h, m]
+// grid: x = split over vertices (chunks of HC), y = tiles of flat k, z = tiles of m
+constexpr int kWgradChunk = 1024;
+template <typename IdxT, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256)
+k_wgrad(const float *__restrict__ X, int64_t ldX, int C, const float *__restrict__ row_scale,
+        const void *__restrict__ nbr, int64_t nbr_ld, int F, int h_host, const int32_t *h_dev,
+        const float *__restrict__ dY, int64_t ldY, const float *__restrict__ act_out, int64_t ldA, int act,
+        int M, float *dWt, float *dbias) {
+  __shared__ float As[BK][BM + 4];  // [h-chunk][flat k]
+  __shared__ float Bs[BK][BN + 4];  // [h-chunk][m]
+  const int H = h_dev ? min(*h_dev, h_host) : h_host;
+  const int K = F * C;
+  const int k0 = blockIdx.y * BM, m0 = blockIdx.z * BN;
+  Tile<BM, BN, TM, TN> T;
+  for (int hc = blockIdx.x * kWgradChunk; hc < H; hc += gridDim.x * kWgradChunk) {
+    T.zero();
+    float bsum = 0.f;
+    const int hend = min(H, hc + kWgradChunk);
+    for (int h0 = hc; h0 < hend; h0 += BK) {
+      for (int u = threadIdx.x; u < BK * BM; u += 256) {
+        const int hh = u / BM, kk = u % BM;
+        const int h = h0 + hh, k = k0 + kk;
+        float v = 0.f;
+        if (h < hend && k < K) {
+          const int f = k / C, c = k - f * C;
+          const int row = nbr ? load_idx<IdxT>(nbr, f * nbr_ld + h) + 1 : h;
+          if (row > 0 || (row == 0 && !nbr)) {
+            v = __ldg(X + (int64_t)row * ldX + c);
+            if (row_scale) v *= __ldg(row_scale + row);
+          }
+        }
+        As[hh][kk] = v;
+      }
+      for (int u = threadIdx.x; u < BK * BN; u += 256) {
+        const int hh = u / BN, mm = u % BN;
+        const int h = h0 + hh, m = m0 + mm;
+        float v = 0.f;
+        if (h < hend && m < M) {
+          v = __ldg(dY + (int64_t)h * ldY + m);
+          if (act_out) v *= act_bwd(__ldg(act_out + (int64_t)h * ldA + m), act);
+        }
+        Bs[hh][mm] = v;
+      }
+      __syncthreads();
+      T.mma(As, Bs);
+      if (dbias && blockIdx.y == 0 && threadIdx.x < BN) {
+#pragma unroll
+        for (int hh = 0; hh < BK; ++hh) bsum += Bs[hh][threadIdx.x];
+      }
+      __syncthreads();
+    }
+    const int tx = threadIdx.x % T.TX, ty = threadIdx.x / T.TX;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int k = k0 + ty * TM + i;
+      if (k >= K) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int m = m0 + tx * TN + j;
+        if (m < M) atomicAdd(dWt + (int64_t)k * M + m, T.acc[i][j]);
+      }
+    }
+    if (dbias && blockIdx.y == 0 && threadIdx.x < BN && m0 + threadIdx.x < M) atomicAdd(dbias + m0 + threadIdx.x, bsum);
+  }
+}
+
+template <typename F>
+int dispatch_idx(int idx_bits, F &&f) {
+  if (idx_bits == 64) return f((int64_t)0);
+  if (idx_bits == 32) return f((int32_t)0);
+  set_error("idx_bits must be 32 or 64, got %d", idx_bits);
+  return EFGH_EINVAL;
+}
+
+}  // namespace
+}  // namespace efgh
+
+using namespace efgh;
+
+extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, int64_t n,
+                                const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
+                                int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream) {
+  EFGH_REQUIRE(C > 0 && n >= 0 && n < (1ll << 30), "efgh_bcl_scatter: bad sizes C=%d n=%lld", C, (long long)n);
+  if (n == 0) return EFGH_OK;
+  EFGH_REQUIRE(feat && w && off && S, "efgh_bcl_scatter: null pointer");
+  const size_t smem = sizeof(float) * ((size_t)C * (kTP + 1) + 4 * kTP) + sizeof(int) * 4 * kTP;
+  EFGH_REQUIRE(smem <= 200 * 1024, "efgh_bcl_scatter: C=%d too large", C);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dispatch_idx(idx_bits, [&](auto tag) -> int {
+    using IdxT = decltype(tag);
+    auto kern = k_scatter<IdxT>;
+    if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for((n + kTP - 1) / kTP, 1, 8), 256, smem, s>>>(feat, stride_c, stride_n, C, (int)n, n_dev, w, w_ld, off,
+                                                                 off_ld, row_shift, S, ldS, wsum);
+    EFGH_LAUNCH_CHECK();
+    return EFGH_OK;
+  });
+}
+
+extern "C" int efgh_bcl_inv_norm(const float *wsum, float *inv, int64_t rows, const int32_t *rows_dev, int rows_extra,
+                                 void *stream) {
+  EFGH_REQUIRE(rows >= 0 && rows < (1ll << 31), "efgh_bcl_inv_norm: bad rows");
+  if (rows == 0) return EFGH_OK;
+  EFGH_REQUIRE(wsum && inv, "efgh_bcl_inv_norm: null pointer");
+  k_inv_norm<<<grid_for(rows, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(wsum, inv, (int)rows, rows_dev,
+                                                                                     rows_extra);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
+}
+
+extern "C" int efgh_bcl_gather(const float *Z, int64_t ldZ, int C, const float *row_scale, int64_t n,
+                               const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
+                               int64_t off_ld, int row_shift, const float *bias, float *out, int64_t stride_c,
+                               int64_t stride_n, void *stream) {
+  EFGH_REQUIRE(C > 0 && n >= 0 && n < (1ll << 30), "efgh_bcl_gather: bad sizes C=%d n=%lld", C, (long long)n);
+  if (n == 0) return EFGH_OK;
+  EFGH_REQUIRE(Z && w && off && out, "efgh_bcl_gather: null pointer");
+  const size_t smem = sizeof(float) * ((size_t)C * (kTP + 1) + 4 * kTP) + sizeof(int) * 4 * kTP;
+  EFGH_REQUIRE(smem <= 200 * 1024, "efgh_bcl_gather: C=%d too large", C);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dispatch_idx(idx_bits, [&](auto tag) -> int {
+    using IdxT = decltype(tag);
+    auto kern = k_gather<IdxT>;
+    if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for((n + kTP - 1) / kTP, 1, 8), 256, smem, s>>>(Z, ldZ, C, row_scale, (int)n, n_dev, w, w_ld, off, off_ld,
+                                                                 row_shift, bias, out, stride_c, stride_n);
+    EFGH_LAUNCH_CHECK();
+    return EFGH_OK;
+  });
+}
+
+extern "C" int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *row_scale, const void *nbr, int idx_bits,
+                             int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *Wt,
+                             const float *bias, int M, int act, float *Y, int64_t ldY, int precision, void *stream) {
+  EFGH_REQUIRE(C > 0 && M > 0 && h >= 0 && h < (1ll << 30), "efgh_bcl_conv: bad sizes");
+  EFGH_REQUIRE(precision == 0, "efgh_bcl_conv: precision %d not available in this build", precision);
+  if (!nbr) F = 1;
+  EFGH_REQUIRE(F >= 1 && F <= 1024, "efgh_bcl_conv: bad filter size %d", F);
+  if (h == 0) return EFGH_OK;
+  EFGH_REQUIRE(X && Wt && Y, "efgh_bcl_conv: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dispatch_idx(idx_bits, [&](auto tag) -> int {
+    using IdxT = decltype(tag);
+    if (M <= 32) {
+      constexpr int BM = 128, BN = 32;
+      dim3 grid(grid_for((h + BM - 1) / BM, 1, 4), (M + BN - 1) / BN);
+      k_conv<IdxT, BM, BN, 4, 4><<<grid, 256, sizeof(int) * F * BM, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev,
+                                                                         Wt, bias, M, act, Y, ldY);
+    } else {
+      constexpr int BM = 64, BN = 64;
+      dim3 grid(grid_for((h + BM - 1) / BM, 1, 4), (M + BN - 1) / BN);
+      k_conv<IdxT, BM, BN, 4, 4><<<grid, 256, sizeof(int) * F * BM, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev,
+                                                                         Wt, bias, M, act, Y, ldY);
+    }
+    EFGH_LAUNCH_CHECK();
+    return EFGH_OK;
+  });
+}
+
+extern "C" int efgh_bcl_conv_dgrad(const float *dY, int64_t ldY, const float *act_out, int64_t ldA, int act, int M,
+                                   const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h,
+                                   const int32_t *h_dev, const float *Wt, int C, float *dX, int64_t ldX, void *stream) {
+  EFGH_REQUIRE(C > 0 && M > 0 && h >= 0 && h < (1ll << 30), "efgh_bcl_conv_dgrad: bad sizes");
+  if (!nbr) F = 1;
+  EFGH_REQUIRE(F >= 1, "efgh_bcl_conv_dgrad: bad filter size %d", F);
+  if (h == 0) return EFGH_OK;
+  EFGH_REQUIRE(dY && Wt && dX, "efgh_bcl_conv_dgrad: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dispatch_idx(idx_bits, [&](auto tag) -> int {
+    using IdxT = decltype(tag);
+    constexpr int BM = 64, BN = 64;
+    dim3 grid(grid_for((h + BM - 1) / BM, 1, 4), (F * C + BN - 1) / BN);
+    k_dgrad<IdxT, BM, BN, 4, 4><<<grid, 256, 0, s>>>(dY, ldY, act_out, ldA, act, M, nbr, nbr_ld, F, (int)h, h_dev, Wt, C, dX,
+                                                     ldX);
+    EFGH_LAUNCH_CHECK();
+    return EFGH_OK;
+  });
+}
+
+extern "C" int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const float *row_scale, const void *nbr,
+                                   int idx_bits, int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev,
+                                   const float *dY, int64_t ldY, const float *act_out, int64_t ldA, int act, int M,
+                                   float *dWt, float *dbias, void *stream) {
+  EFGH_REQUIRE(C > 0 && M > 0 && h >= 0 && h < (1ll << 30), "efgh_bcl_conv_wgrad: bad sizes");
+  if (!nbr) F = 1;
+  EFGH_REQUIRE(F >= 1, "efgh_bcl_conv_wgrad: bad filter size %d", F);
+  if (h == 0) return EFGH_OK;
+  EFGH_REQUIRE(X && dY && dWt, "efgh_bcl_conv_wgrad: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dispatch_idx(idx_bits, [&](auto tag) -> int {
+    using IdxT = decltype(tag);
+    constexpr int BM = 64, BN = 64;
+    int gx = (int)((h + kWgradChunk - 1) / kWgradChunk);
+    if (gx > 1024) gx = 1024;
+    dim3 grid(gx, (F * C + BM - 1) / BM, (M + BN - 1) / BN);
+    k_wgrad<IdxT, BM, BN, 4, 4><<<grid, 256, 0, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev, dY, ldY, act_out,
+                                                     ldA, act, M, dWt, dbias);
+    EFGH_LAUNCH_CHECK();
+    return EFGH_OK;
+  });
+}

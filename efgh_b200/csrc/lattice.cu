@@ -1,0 +1,497 @@
+// Permutohedral lattice build on the GPU (d = 3).
+//
+// Replaces, per level, reference nets/generate_data.py:128-179 + nets/transforms.py:125-184:
+//   k_clear    reset the hash table / scan state, latch the device-side point count
+//   k_points   elevate -> round -> rank -> barycentric -> 4 simplex keys per point
+//              (generate_data.py:56-112), key box (:135-136), hash insert keeping per key the
+//              SMALLEST stream position p = 4*point + remainder (the order transforms.py:152-166 walks)
+//   k_assign   single-pass decoupled-look-back scan over "p is the first occurrence of its key":
+//              rank among first occurrences == the reference's insertion index hash_cnt1
+//   k_vertices lattice offsets per point, blur neighbours per vertex (transforms.py:168-180, including
+//              key2int's mixed-radix aliasing for keys outside the key box), next-level coordinates
+//              (generate_data.py:175-178)
+//
+// Data layout in HBM (all sized by the caller through efgh_lattice_workspace_bytes):
+//   tkeys  u64[T]   packed key per table slot (3 coordinates x 21 bits; the 4th is minus their sum)
+//   tmin   i32[T]   smallest stream position that inserted the key
+//   tval   i32[T]   vertex index of the key (valid after k_assign)
+//   slots  int4[n]  table slot of each of the point's 4 keys (so later passes never re-probe)
+//   vkeys  u64[4n]  packed key of vertex h, insertion order
+//   tiles  u64[..]  look-back status words
+// T = power of two >= 8 * n (load factor <= 0.5 even when every key is distinct), so for one 131k-point
+// scan the whole table (16 MB) stays resident in the 126 MB L2 and the random probes never reach HBM.
+//
+// Float semantics are part of the contract (keys must be bit-exact): every operation below is an
+// explicit round-to-nearest intrinsic so that nvcc cannot contract or reassociate it; the chain
+// reproduces MKL sgemm's k-ascending FMA order that the reference's torch.matmul resolves to.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace efgh {
+
+namespace {
+
+constexpr int kBias = 1 << 20;
+constexpr unsigned long long kEmpty = ~0ull;
+constexpr int kPointThreads = 256;
+constexpr int kTile = 512;  // points per scan tile (4 keys each)
+
+struct Workspace {
+  unsigned long long *tkeys;
+  int *tmin;
+  int *tval;
+  int4 *slots;
+  unsigned long long *vkeys;
+  unsigned long long *tiles;
+  int64_t table_cap;
+  size_t bytes;
+};
+
+inline int64_t pow2_ceil(int64_t v) {
+  int64_t p = 1024;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+Workspace carve(void *base, int64_t n_cap) {
+  Workspace w;
+  if (n_cap < 1) n_cap = 1;
+  w.table_cap = pow2_ceil(8 * n_cap);
+  size_t off = 0;
+  char *b = static_cast<char *>(base);
+  w.tkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * w.table_cap);
+  w.tmin = reinterpret_cast<int *>(b + off); off = align_up(off + sizeof(int) * w.table_cap);
+  w.tval = reinterpret_cast<int *>(b + off); off = align_up(off + sizeof(int) * w.table_cap);
+  w.slots = reinterpret_cast<int4 *>(b + off); off = align_up(off + sizeof(int4) * n_cap);
+  w.vkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * 4 * n_cap);
+  w.tiles = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * ((n_cap + kTile - 1) / kTile + 1));
+  w.bytes = off;
+  return w;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(int k0, int k1, int k2) {
+  return ((unsigned long long)(unsigned)(k0 + kBias) << 42) | ((unsigned long long)(unsigned)(k1 + kBias) << 21) |
+         (unsigned long long)(unsigned)(k2 + kBias);
+}
+
+__device__ __forceinline__ void unpack_key(unsigned long long p, int &k0, int &k1, int &k2) {
+  k0 = (int)((p >> 42) & 0x1fffff) - kBias;
+  k1 = (int)((p >> 21) & 0x1fffff) - kBias;
+  k2 = (int)(p & 0x1fffff) - kBias;
+}
+
+__device__ __forceinline__ unsigned hash_key(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (unsigned)k;
+}
+
+// table size for n points: power of two >= 8n (>= 1024), never above the carved capacity
+__device__ __forceinline__ int table_mask_for(int n, int64_t table_cap) {
+  long long want = 8ll * n;
+  long long t = 1024;
+  while (t < want && t < table_cap) t <<= 1;
+  return (int)(t - 1);
+}
+
+__global__ void k_clear(efgh_lattice_state *st, const int32_t *n_dev, int n_host, int64_t table_cap,
+                        unsigned long long *tkeys, int *tmin, unsigned long long *tiles, int n_tiles_cap) {
+  int n = n_dev ? min(max(*n_dev, 0), n_host) : n_host;
+  int mask = table_mask_for(n, table_cap);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i <= mask; i += stride) {
+    tkeys[i] = kEmpty;
+    tmin[i] = 0x7fffffff;
+  }
+  int n_tiles = (n + kTile - 1) / kTile;
+  for (int64_t i = tid; i < n_tiles && i < n_tiles_cap; i += stride) tiles[i] = 0ull;
+  if (tid == 0) {
+    st->n = n;
+    st->hash_cnt = 0;
+    st->status = 0;
+    st->table_mask = mask;
+    for (int c = 0; c < 4; ++c) {
+      st->key_min[c] = 0x7fffffff;
+      st->key_max[c] = -0x7fffffff - 1;
+    }
+    st->tile_counter = 0;
+  }
+}
+
+// Elevation matrix E (4x3) as float32 bit patterns (generate_data.py:15-20) and
+// expected_std = 4*sqrt(2/3) (generate_data.py:19) rounded to float32.
+#define EFGH_E_A __int_as_float(0x3f3504f3)   //  0.70710677  1/sqrt(2)
+#define EFGH_E_B __int_as_float(0x3ed105eb)   //  0.40824828  1/sqrt(6)
+#define EFGH_E_C __int_as_float(0x3e93cd3a)   //  0.28867513  1/sqrt(12)
+#define EFGH_E_B2 __int_as_float(0xbf5105eb)  // -2/sqrt(6)
+#define EFGH_E_C3 __int_as_float(0xbf5db3d7)  // -3/sqrt(12) (rounded product)
+#define EFGH_STD __int_as_float(0x405105ec)   //  3.2659864
+
+__device__ __forceinline__ int canonical(int i, int j) { return (j <= 3 - i) ? j : j - 4; }
+
+__global__ void __launch_bounds__(kPointThreads)
+k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__restrict__ bary,
+         float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, unsigned long long *tkeys,
+         int *tmin, int4 *slots) {
+  const int n = st->n;
+  const unsigned mask = (unsigned)st->table_mask;
+  int kmin[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  int kmax[4] = {-0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1};
+  int bad = 0;
+
+  const float E[4][3] = {{EFGH_E_A, EFGH_E_B, EFGH_E_C},
+                         {-EFGH_E_A, EFGH_E_B, EFGH_E_C},
+                         {0.0f, EFGH_E_B2, EFGH_E_C},
+                         {0.0f, 0.0f, EFGH_E_C3}};
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = __fmul_rn(__ldg(pts + a * pts_ld + i), scale);  // generate_data.py:130
+    float el[4], gr[4], d0[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = __fmul_rn(E[c][0], p[0]);                  // :67 k-ascending FMA chain (MKL sgemm)
+      acc = __fmaf_rn(E[c][1], p[1], acc);
+      acc = __fmaf_rn(E[c][2], p[2], acc);
+      el[c] = __fmul_rn(acc, EFGH_STD);
+      gr[c] = __fmul_rn(rintf(__fmul_rn(el[c], 0.25f)), 4.0f);  // :70 (x/4 == x*0.25 exactly)
+      d0[c] = __fsub_rn(el[c], gr[c]);                       // :72
+    }
+    int rank[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                            // :73-78 stable descending sort, inverted
+      int r = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r += (d0[j] > d0[c]) || (d0[j] == d0[c] && j < c);
+      rank[c] = r;
+    }
+    const int rs = (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(gr[0], gr[1]), gr[2]), gr[3]), 0.25f);  // :81
+    float b[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float diff[4];
+    int gi[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                            // :83-93
+      if (rs > 0 && rank[c] >= 4 - rs) { gr[c] = __fsub_rn(gr[c], 4.0f); rank[c] -= 4; }
+      else if (rs < 0 && rank[c] < -rs) { gr[c] = __fadd_rn(gr[c], 4.0f); rank[c] += 4; }
+      rank[c] += rs;
+      diff[c] = __fsub_rn(el[c], gr[c]);                     // :96
+      if (!(fabsf(gr[c]) < (float)(kBias - 8))) { bad = 1; gr[c] = 0.f; }
+      gi[c] = (int)gr[c];                                    // :97
+      rank[c] &= 3;                                          // only reachable for non-finite input
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                            // :100 slot 3-rank gets +diff
+#pragma unroll
+      for (int s = 0; s < 4; ++s) if (3 - rank[c] == s) b[s] = __fadd_rn(b[s], diff[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                            // :101 slot 4-rank gets -diff
+#pragma unroll
+      for (int s = 1; s < 5; ++s) if (4 - rank[c] == s) b[s] = __fsub_rn(b[s], diff[c]);
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) b[s] = __fmul_rn(b[s], 0.25f);   // :102
+    b[0] = __fadd_rn(b[0], __fadd_rn(1.0f, b[4]));               // :103
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      bary[c * out_ld + i] = b[c];
+      elmgr[c * out_ld + i] = diff[c];
+    }
+
+    int s4[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                            // :106 keys[c, n, r] = greedy[c] + canonical[rank[c], r]
+      int k[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        k[c] = gi[c] + canonical(rank[c], r);
+        kmin[c] = min(kmin[c], k[c]);
+        kmax[c] = max(kmax[c], k[c]);
+      }
+      const unsigned long long key = pack_key(k[0], k[1], k[2]);
+      unsigned h = hash_key(key) & mask;
+      unsigned probes = 0;
+      while (true) {
+        unsigned long long cur = tkeys[h];
+        if (cur != key) {
+          if (cur == kEmpty) cur = atomicCAS(&tkeys[h], kEmpty, key);
+          if (cur != kEmpty && cur != key) {
+            h = (h + 1) & mask;
+            if (++probes > mask) { bad |= 4; break; }
+            continue;
+          }
+        }
+        break;
+      }
+      atomicMin(&tmin[h], 4 * i + r);
+      s4[r] = (int)h;
+    }
+    slots[i] = make_int4(s4[0], s4[1], s4[2], s4[3]);
+  }
+
+  // key box: warp shuffle -> shared -> 8 global atomics per CTA
+  __shared__ int s_min[4][kPointThreads / 32], s_max[4][kPointThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int mn = warp_reduce_min(kmin[c]), mx = warp_reduce_max(kmax[c]);
+    if (lane == 0) { s_min[c][wid] = mn; s_max[c][wid] = mx; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    int c = threadIdx.x, mn = s_min[c][0], mx = s_max[c][0];
+    for (int w = 1; w < kPointThreads / 32; ++w) { mn = min(mn, s_min[c][w]); mx = max(mx, s_max[c][w]); }
+    if (mn <= mx) { atomicMin(&st->key_min[c], mn); atomicMax(&st->key_max[c], mx); }
+  }
+  if (bad) atomicOr(&st->status, (bad & 1 ? EFGH_ST_KEY_RANGE : 0) | (bad & 4 ? EFGH_ST_TABLE_FULL : 0));
+}
+
+// Single-pass scan (decoupled look-back) over first-occurrence flags; one point (4 keys) per thread.
+// status word: bits 63..62 = 1 aggregate ready / 2 inclusive prefix ready, low 32 bits = value.
+__global__ void __launch_bounds__(kTile)
+k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__restrict__ tmin,
+         int *__restrict__ tval, const unsigned long long *__restrict__ tkeys,
+         unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap) {
+  __shared__ int s_tile, s_prefix;
+  __shared__ int s_warp[kTile / 32];
+  const int n = st->n;
+  const int n_tiles = (n + kTile - 1) / kTile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= n_tiles) return;
+
+  const int i = tile * kTile + threadIdx.x;
+  int4 s = make_int4(0, 0, 0, 0);
+  int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+  if (i < n) {
+    s = slots[i];
+    f0 = tmin[s.x] == 4 * i;
+    f1 = tmin[s.y] == 4 * i + 1;
+    f2 = tmin[s.z] == 4 * i + 2;
+    f3 = tmin[s.w] == 4 * i + 3;
+  }
+  const int cnt = f0 + f1 + f2 + f3;
+  // block exclusive scan of cnt
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int v = lane < kTile / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane < kTile / 32) s_warp[lane] = v;  // inclusive warp totals
+  }
+  __syncthreads();
+  const int block_total = s_warp[kTile / 32 - 1];
+  const int local = inc - cnt + (wid ? s_warp[wid - 1] : 0);
+
+  if (threadIdx.x == 0) {
+    int prefix = 0;
+    volatile unsigned long long *vt = tiles;
+    if (tile > 0) {
+      vt[tile] = (1ull << 62) | (unsigned)block_total;
+      for (int j = tile - 1; j >= 0; --j) {
+        unsigned long long w;
+        do { w = vt[j]; } while ((w >> 62) == 0);
+        prefix += (int)(unsigned)(w & 0xffffffffu);
+        if ((w >> 62) == 2) break;
+      }
+    }
+    __threadfence();
+    vt[tile] = (2ull << 62) | (unsigned)(prefix + block_total);
+    s_prefix = prefix;
+    if (tile == n_tiles - 1) {
+      const int total = prefix + block_total;
+      st->hash_cnt = total;
+      if (total > h_cap) atomicOr(&st->status, EFGH_ST_VERTEX_CAP);
+    }
+  }
+  __syncthreads();
+  int idx = s_prefix + local;
+  if (f0) { tval[s.x] = idx; vkeys[idx] = tkeys[s.x]; ++idx; }
+  if (f1) { tval[s.y] = idx; vkeys[idx] = tkeys[s.y]; ++idx; }
+  if (f2) { tval[s.z] = idx; vkeys[idx] = tkeys[s.z]; ++idx; }
+  if (f3) { tval[s.w] = idx; vkeys[idx] = tkeys[s.w]; ++idx; }
+}
+
+__device__ __forceinline__ int table_find(const unsigned long long *__restrict__ tkeys,
+                                          const int *__restrict__ tval, unsigned mask, unsigned long long key) {
+  unsigned h = hash_key(key) & mask;
+  for (unsigned probes = 0; probes <= mask; ++probes) {
+    unsigned long long cur = tkeys[h];
+    if (cur == key) return tval[h];
+    if (cur == kEmpty) return -1;
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ long long floor_mod64(long long a, long long b) {
+  long long m = a % b;
+  return (m != 0 && ((m < 0) != (b < 0))) ? m + b : m;
+}
+
+__global__ void __launch_bounds__(256)
+k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
+           const int *__restrict__ tval, const unsigned long long *__restrict__ tkeys,
+           const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
+           int64_t off_ld, const int32_t *__restrict__ foffs, int F, int64_t *__restrict__ nbr,
+           int32_t *__restrict__ nbr32, int64_t nbr_ld, float *__restrict__ next_pts, int64_t next_ld,
+           float next_divisor) {
+  const int n = min(st->n, n_cap);
+  const int H = min(st->hash_cnt, h_cap);
+  const unsigned mask = (unsigned)st->table_mask;
+  const int stride = gridDim.x * blockDim.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+
+  // lattice offsets: pc1_lattice_offset[r, n] = vertex index of the point's r-th key (transforms.py:166)
+  if (loff || loff32) {
+    for (int i = tid; i < n; i += stride) {
+      const int4 s = slots[i];
+      const int v0 = tval[s.x], v1 = tval[s.y], v2 = tval[s.z], v3 = tval[s.w];
+      if (loff) {
+        loff[i] = v0; loff[off_ld + i] = v1; loff[2 * off_ld + i] = v2; loff[3 * off_ld + i] = v3;
+      }
+      if (loff32) {
+        loff32[i] = v0; loff32[off_ld + i] = v1; loff32[2 * off_ld + i] = v2; loff32[3 * off_ld + i] = v3;
+      }
+    }
+  }
+
+  int kmin[4], kmax[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { kmin[c] = st->key_min[c]; kmax[c] = st->key_max[c]; }
+  const float E[4][3] = {{EFGH_E_A, EFGH_E_B, EFGH_E_C},
+                         {-EFGH_E_A, EFGH_E_B, EFGH_E_C},
+                         {0.0f, EFGH_E_B2, EFGH_E_C},
+                         {0.0f, 0.0f, EFGH_E_C3}};
+
+  for (int h = tid; h < H; h += stride) {
+    int k[4];
+    unpack_key(vkeys[h], k[0], k[1], k[2]);
+    k[3] = -(k[0] + k[1] + k[2]);
+    if (F > 0 && (nbr || nbr32)) {
+      for (int f = 0; f < F; ++f) {
+        const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
+        int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
+        bool in_box = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) in_box = in_box && q[c] >= kmin[c] && q[c] <= kmax[c];
+        int res;
+        if (in_box) {
+          res = (q[0] + q[1] + q[2] + q[3] == 0) ? table_find(tkeys, tval, mask, pack_key(q[0], q[1], q[2])) : -1;
+        } else {
+          // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
+          // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
+          const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
+                          s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
+          long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
+                        (q[3] - kmin[3]);
+          res = -1;
+          if (P >= 0 && P < s0 * s1 * s2 * s3) {
+            const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
+            const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
+            const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
+            const int r0 = (int)P + kmin[0], r1 = (int)a1 + kmin[1], r2 = (int)a2 + kmin[2], r3 = (int)a3 + kmin[3];
+            if (r0 + r1 + r2 + r3 == 0) res = table_find(tkeys, tval, mask, pack_key(r0, r1, r2));
+          }
+        }
+        if (nbr) nbr[f * nbr_ld + h] = res;
+        if (nbr32) nbr32[f * nbr_ld + h] = res;
+      }
+    }
+    if (next_pts) {                                          // generate_data.py:177-178
+      float q[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) q[c] = __fdiv_rn((float)k[c], next_divisor);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float acc = __fmul_rn(E[0][a], q[0]);
+        acc = __fmaf_rn(E[1][a], q[1], acc);
+        acc = __fmaf_rn(E[2][a], q[2], acc);
+        acc = __fmaf_rn(E[3][a], q[3], acc);
+        next_pts[a * next_ld + h] = acc;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace efgh
+
+using namespace efgh;
+
+extern "C" size_t efgh_lattice_workspace_bytes(int64_t n_cap) { return carve(nullptr, n_cap).bytes; }
+
+extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
+                                   float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap,
+                                   efgh_lattice_state *state, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+  EFGH_REQUIRE(n >= 0 && n < (1ll << 28), "efgh_lattice_points: n=%lld out of range", (long long)n);
+  EFGH_REQUIRE(state && workspace && (n == 0 || (pts && barycentric && el_minus_gr)), "efgh_lattice_points: null pointer");
+  EFGH_REQUIRE(pts_ld >= n && out_ld >= n, "efgh_lattice_points: leading dimension smaller than n");
+  Workspace w = carve(workspace, n);
+  if (w.bytes > workspace_bytes) {
+    set_error("efgh_lattice_points: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    return EFGH_ENOMEM;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_tiles_cap = (int)((n + kTile - 1) / kTile) + 1;
+  k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.tkeys, w.tmin, w.tiles,
+                                                         n_tiles_cap);
+  EFGH_LAUNCH_CHECK();
+  if (n == 0) return EFGH_OK;
+  k_points<<<grid_for(n, kPointThreads, 8), kPointThreads, 0, s>>>(pts, pts_ld, scale, barycentric, el_minus_gr,
+                                                                   out_ld, state, w.tkeys, w.tmin, w.slots);
+  EFGH_LAUNCH_CHECK();
+  k_assign<<<(int)((n + kTile - 1) / kTile), kTile, 0, s>>>(state, w.slots, w.tmin, w.tval, w.tkeys, w.vkeys, w.tiles,
+                                                            (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30)));
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
+}
+
+extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                                     const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
+                                     int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
+                                     float next_divisor, efgh_lattice_state *state, void *workspace,
+                                     size_t workspace_bytes, void *stream) {
+  EFGH_REQUIRE(n >= 0 && n < (1ll << 28) && h >= 0 && h < (1ll << 30), "efgh_lattice_vertices: sizes out of range");
+  EFGH_REQUIRE(state && workspace, "efgh_lattice_vertices: null pointer");
+  EFGH_REQUIRE(F <= 0 || filter_offsets, "efgh_lattice_vertices: filter_offsets is null");
+  EFGH_REQUIRE((!lattice_offset && !lattice_offset32) || off_ld >= n, "efgh_lattice_vertices: off_ld < n");
+  EFGH_REQUIRE((!blur_neighbors && !blur_neighbors32) || nbr_ld >= h, "efgh_lattice_vertices: nbr_ld < h");
+  EFGH_REQUIRE(!next_pts || next_ld >= h, "efgh_lattice_vertices: next_ld < h");
+  Workspace w = carve(workspace, n);
+  if (w.bytes > workspace_bytes) {
+    set_error("efgh_lattice_vertices: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    return EFGH_ENOMEM;
+  }
+  if (n == 0) return EFGH_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t items = n > h ? n : h;
+  k_vertices<<<grid_for(items, 256, 8), 256, 0, s>>>(state, (int)n, (int)h, w.slots, w.tval, w.tkeys, w.vkeys,
+                                                     lattice_offset, lattice_offset32, off_ld, filter_offsets, F,
+                                                     blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
+                                                     next_divisor);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
+}

@@ -1,0 +1,161 @@
+/* efgh_b200 - C ABI of the B200-native permutohedral-lattice / bilateral-convolution hot path.
+ *
+ * This is the drop-in boundary.  In the reference the only native FFI on this path is
+ * the per-key hash map
+ *     void*     khash_int2int_init(void);                          reference lib/khash_int2int.h:8
+ *     void      khash_int2int_destroy(void*);                      reference lib/khash_int2int.h:12
+ *     khint64_t khash_int2int_get(void*, khint64_t, khint64_t);    reference lib/khash_int2int.h:17
+ *     int       khash_int2int_set(void*, khint64_t, khint64_t);    reference lib/khash_int2int.h:24
+ * declared for cffi at reference lib/build_khash_cffi.py:6-13 and called one key at a time from numba
+ * (reference nets/transforms.py:9-15,125-184).  A GPU cannot be fed through a per-key call, so the
+ * boundary moves up one level: each entry point below replaces one whole reference function, cited at
+ * its declaration.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain pointers + sizes only;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no call synchronises;
+ *   - the library never allocates device memory: outputs and workspaces are caller-allocated;
+ *   - counts that the reference returns as Python ints (pc1_hash_cnt) live in device memory so that a
+ *     whole 5-level scan can be enqueued (or graph-captured) without a host round trip.  Every
+ *     `*_dev` count argument may be NULL, in which case the host-side value next to it is exact;
+ *     otherwise the host-side value is a CAPACITY and the kernel reads the true count on the device;
+ *   - matrices are passed with explicit leading dimensions (element strides) so that tensors narrowed
+ *     from over-allocated buffers can be used in place;
+ *   - return value: 0 on success, a negative EFGH_E* code otherwise; efgh_last_error() gives the text
+ *     (thread-local).  No CPU fallback exists: without a CUDA device every compute entry point fails.
+ *   - only lattice dimension d = 3 (d+1 = 4) is implemented - the only value EFGHNet uses
+ *     (reference configs/train_rellis.yaml:28).
+ */
+#ifndef EFGH_B200_H
+#define EFGH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFGH_OK 0
+#define EFGH_EINVAL (-1)   /* bad argument */
+#define EFGH_ECUDA (-2)    /* CUDA runtime error (text in efgh_last_error) */
+#define EFGH_ENOMEM (-3)   /* workspace too small */
+
+/* bits of the per-level device status word (efgh_lattice_state.status) */
+#define EFGH_ST_KEY_RANGE 1   /* a lattice coordinate fell outside +-2^20: cloud far outside the supported box */
+#define EFGH_ST_VERTEX_CAP 2  /* more distinct vertices than the caller's capacity */
+#define EFGH_ST_TABLE_FULL 4  /* hash table capacity exhausted (workspace sized for fewer points) */
+
+/* Device-resident per-level record; the caller may copy it back (24 x int32) after the level. */
+typedef struct {
+  int32_t n;          /* points that entered the level */
+  int32_t hash_cnt;   /* distinct lattice vertices = reference pc1_hash_cnt (generate_data.py:139) */
+  int32_t status;     /* EFGH_ST_* bits, 0 = ok */
+  int32_t table_mask; /* internal */
+  int32_t key_min[4]; /* reference key_mins (generate_data.py:136) */
+  int32_t key_max[4]; /* reference key_maxs (generate_data.py:135) */
+  int32_t tile_counter;
+  int32_t reserved[11];
+} efgh_lattice_state;
+
+const char *efgh_last_error(void);
+int efgh_version(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int efgh_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lattice build.  Together efgh_lattice_points + efgh_lattice_vertices replace one iteration of the
+ * loop in GenerateData.__call__ (reference nets/generate_data.py:128-184): get_keys_and_barycentric
+ * (:56-112), the key box (:135-136), the unique count (:138-139), numba build_it
+ * (reference nets/transforms.py:125-184) with its two khash tables, and the next-level coordinates
+ * (:175-178).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace one level needs for up to n_cap input points (and up to 4*n_cap key slots). */
+size_t efgh_lattice_workspace_bytes(int64_t n_cap);
+
+/* Phase 1: per-point elevation / rank / barycentric weights (generate_data.py:56-112), insertion of
+ * the 4 simplex vertices of every point into a device hash table that keeps, per key, the smallest
+ * position in the point-major / remainder-minor stream (the order build_it walks, transforms.py:152-166),
+ * then a single-pass scan over first occurrences -> insertion-ordered vertex indices.
+ *   pts (3,n) rows with stride pts_ld, multiplied by `scale` first (generate_data.py:130);
+ *   barycentric, el_minus_gr: (4,n) f32 rows with stride out_ld;
+ *   state: device record, fully written by this call (state->hash_cnt = number of vertices);
+ *   h_cap: capacity the caller will give the vertex-side arrays (status bit if exceeded). */
+int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
+                        float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap,
+                        efgh_lattice_state *state, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Phase 2 (needs phase 1's workspace intact): per-point lattice offsets, per-vertex blur neighbours
+ * and next-level coordinates.
+ *   lattice_offset (4,n) int64 / lattice_offset32 (4,n) int32, rows with stride off_ld (either may be
+ *     NULL): pc1_lattice_offset (transforms.py:166);
+ *   filter_offsets (F,4) int32 on the device, the reference's traversal order
+ *     (reference nets/transforms.py:95-122); F <= 0 skips the neighbour table (radius -1);
+ *   blur_neighbors (F,h) int64 / blur_neighbors32 (F,h) int32, rows with stride nbr_ld (either may be
+ *     NULL); entry -1 = vertex absent, exactly as khash_int2int_get(..., -1) on the packed key
+ *     (transforms.py:168-180), including the mixed-radix aliasing of keys outside the key box;
+ *   next_pts (3,h) f32 rows with stride next_ld or NULL: E^T (key / next_divisor)
+ *     (generate_data.py:177-178), next_divisor = float(expected_std * scale);
+ *   n, h: capacities of the point / vertex side arrays; the true counts are read from `state`. */
+int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                          const int32_t *filter_offsets, int F, int64_t h,
+                          int64_t *blur_neighbors, int32_t *blur_neighbors32, int64_t nbr_ld,
+                          float *next_pts, int64_t next_ld, float next_divisor,
+                          efgh_lattice_state *state, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bilateral convolution layer pieces (reference nets/bilateralNN.py:148-263).  Lattice-side feature
+ * matrices are VERTEX-MAJOR: row h holds the C channels of vertex h (row 0 of a "sink" matrix is the
+ * all-zero row that absent neighbours (-1) read, bilateralNN.py:183-184).  Point-side matrices are
+ * addressed as base[c*stride_c + n*stride_n] so both the reference's (C,N) layout and a point-major
+ * layout work.  idx_bits is 64 (reference int64 tensors) or 32.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Splat (bilateralNN.py:176-191) and its density normaliser (:193-211); also the adjoint of slice.
+ *   S[(off[r,n]+row_shift), c] += w[r,n] * feat[c,n];  wsum[(off[r,n]+row_shift)] += w[r,n] (if wsum)
+ *   S is (rows, C) with leading dimension ldS; the caller zero-fills S and wsum beforehand. */
+int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, int64_t n,
+                     const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
+                     int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream);
+
+/* inv[r] = 1 / (wsum[r] + 1e-5)   (bilateralNN.py:210) for r < rows (rows_dev + rows_extra if given) */
+int efgh_bcl_inv_norm(const float *wsum, float *inv, int64_t rows, const int32_t *rows_dev, int rows_extra,
+                      void *stream);
+
+/* Slice (bilateralNN.py:251-261) and the adjoint of splat:
+ *   out[c,n] = sum_r w[r,n] * Z[off[r,n]+row_shift, c] * (row_scale ? row_scale[row] : 1) + (bias ? bias[c] : 0) */
+int efgh_bcl_gather(const float *Z, int64_t ldZ, int C, const float *row_scale, int64_t n, const int32_t *n_dev,
+                    const float *w, int64_t w_ld, const void *off, int idx_bits, int64_t off_ld, int row_shift,
+                    const float *bias, float *out, int64_t stride_c, int64_t stride_n, void *stream);
+
+/* Lattice convolution (bilateralNN.py:240-244): gather the F neighbours of each vertex and contract.
+ *   Y[h, m] = act( bias[m] + sum_{f,c} Wt[(f*C + c), m] * X[nbr[f,h]+1, c] * (row_scale ? row_scale[row] : 1) )
+ *   X (rows, C) vertex-major with leading dimension ldX, row 0 = sink; nbr (F,h) rows with stride nbr_ld.
+ *   nbr == NULL means F = 1 and row = h (a 1x1 convolution over a matrix WITHOUT sink row).
+ *   Wt is the reference weight (M, C, F, 1) re-laid as (F*C, M) row-major (done once per weight update
+ *   by the host module).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).  Y (h, M) leading dimension ldY.
+ *   precision: 0 = fp32 FFMA (CUDA cores); other values are reserved for the tensor-core paths. */
+int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *row_scale, const void *nbr, int idx_bits,
+                  int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *Wt, const float *bias,
+                  int M, int act, float *Y, int64_t ldY, int precision, void *stream);
+
+/* Backward of efgh_bcl_conv w.r.t. its input: dX[nbr[f,h]+1, c] += sum_m dY[h,m] * Wt[(f*C+c), m]
+ * (absent neighbours are skipped; nbr == NULL: dX[h, c] = ..., plain store).  If act_out != NULL the
+ * incoming gradient is first masked by the forward activation: dY *= act'(act_out) where act_out is
+ * the forward OUTPUT (ReLU: >0 ? 1 : 0, Leaky: >0 ? 1 : 0.1).  The caller zero-fills dX when nbr != NULL. */
+int efgh_bcl_conv_dgrad(const float *dY, int64_t ldY, const float *act_out, int64_t ldA, int act, int M,
+                        const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev,
+                        const float *Wt, int C, float *dX, int64_t ldX, void *stream);
+
+/* Backward of efgh_bcl_conv w.r.t. weights and bias (both accumulate into zero-filled outputs):
+ *   dWt[(f*C+c), m] += sum_h X[nbr[f,h]+1, c] * row_scale[row] * dYm[h, m];  dbias[m] += sum_h dYm[h,m]
+ *   with dYm = dY masked by the activation as above. */
+int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const float *row_scale, const void *nbr, int idx_bits,
+                        int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *dY, int64_t ldY,
+                        const float *act_out, int64_t ldA, int act, int M, float *dWt, float *dbias, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFGH_B200_H */

@@ -1,0 +1,93 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/efgh_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from efgh_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    _capi.build()
+    return ctypes.CDLL(_capi.LIB_PATH)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "efgh_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(efgh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for must in ("efgh_lattice_points", "efgh_lattice_vertices", "efgh_bcl_scatter", "efgh_bcl_gather",
+                 "efgh_bcl_conv", "efgh_bcl_conv_dgrad", "efgh_bcl_conv_wgrad", "efgh_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(library):
+    for name in declared_symbols():
+        assert hasattr(library, name), "libefgh_b200.so does not export %s" % name
+
+
+def test_binding_covers_header():
+    assert sorted(_capi.SIGNATURES) == declared_symbols()
+
+
+def test_binding_arity_matches_header():
+    text = open(os.path.join(ROOT, "include", "efgh_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, (_, args) in _capi.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, text, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, binding %d" % (name, n, len(args))
+
+
+def test_pure_host_entry_points(library):
+    # no compute calls without a GPU: only the size query and the error string
+    library.efgh_lattice_workspace_bytes.restype = ctypes.c_size_t
+    library.efgh_lattice_workspace_bytes.argtypes = [ctypes.c_int64]
+    small = library.efgh_lattice_workspace_bytes(1000)
+    big = library.efgh_lattice_workspace_bytes(131072)
+    assert 0 < small < big < 64 * 1024 * 1024
+    library.efgh_version.restype = ctypes.c_int
+    assert library.efgh_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """The product modules refuse CPU devices instead of silently computing elsewhere."""
+    import torch
+    from efgh_b200.generate_data import GenerateData
+    from efgh_b200.bilateralNN import BilateralConvFlex
+    with pytest.raises(Exception):
+        GenerateData(3, [[1.0, 1]], "cpu")
+    m = BilateralConvFlex(3, 1, 4, [4, 4], "cpu", True, True, True, True, False, False)
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 4, 8), torch.zeros(1, 4, 8), torch.zeros(1, 4, 8, dtype=torch.long),
+          torch.zeros(1, 15, 3, dtype=torch.long), None, None)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "efgh_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").lower() or f == "__init__.py" or \
+                    "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_state_dict_keys_match_reference_layout():
+    from efgh_b200.bilateralNN import BilateralConvFlex
+    m = BilateralConvFlex(3, 1, 36, [32, 32], "cuda", True, True, True, True, False, False, chunk_size=-1)
+    sd = m.state_dict()
+    assert list(sd) == ["feat_indices", "blur_conv.0.weight", "blur_conv.0.bias", "blur_conv.2.weight", "blur_conv.2.bias"]
+    assert tuple(sd["blur_conv.0.weight"].shape) == (32, 36, 15, 1) and tuple(sd["blur_conv.2.weight"].shape) == (32, 32, 1, 1)
+    m2 = BilateralConvFlex(3, 1, 8, [16, 9], "cuda", True, True, True, True, True, True)
+    assert "bias" in m2.state_dict() and "out_indices" in m2.state_dict()

@@ -82,6 +82,22 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C, int n_h
   }
 }
 
+__global__ void k_zero(float *__restrict__ S, int64_t ldS, int C, float *__restrict__ wsum, int rows_host,
+                       const int32_t *rows_dev, int rows_extra) {
+  const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ldS == C && C % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
+    float4 *S4 = reinterpret_cast<float4 *>(S);
+    const int64_t total = (int64_t)rows * C / 4;
+    for (int64_t i = tid; i < total; i += stride) S4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const int64_t total = (int64_t)rows * C;
+    for (int64_t i = tid; i < total; i += stride) S[(i / C) * ldS + (i % C)] = 0.f;
+  }
+  if (wsum)
+    for (int64_t i = tid; i < rows; i += stride) wsum[i] = 0.f;
+}
+
 __global__ void k_inv_norm(const float *__restrict__ wsum, float *__restrict__ inv, int rows_host,
                            const int32_t *rows_dev, int rows_extra) {
   const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
@@ -458,6 +474,17 @@ extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t str
     EFGH_LAUNCH_CHECK();
     return EFGH_OK;
   });
+}
+
+extern "C" int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, int64_t rows_cap, const int32_t *rows_dev,
+                             int rows_extra, void *stream) {
+  EFGH_REQUIRE(C > 0 && ldS >= C && rows_cap >= 0 && rows_cap < (1ll << 31), "efgh_bcl_zero: bad sizes");
+  if (rows_cap == 0) return EFGH_OK;
+  EFGH_REQUIRE(S, "efgh_bcl_zero: null pointer");
+  k_zero<<<grid_for(rows_cap * C / 4, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ldS, C, wsum, (int)rows_cap,
+                                                                                         rows_dev, rows_extra);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
 }
 
 extern "C" int efgh_bcl_inv_norm(const float *wsum, float *inv, int64_t rows, const int32_t *rows_dev, int rows_extra,

@@ -36,6 +36,10 @@ class LatticeStatusError(RuntimeError):
     pass
 
 
+class VertexCapExceeded(LatticeStatusError):
+    pass
+
+
 def check_status(status, level):
     if status:
         why = []
@@ -98,9 +102,13 @@ class GenerateData(object):
             dev = pc1.device if pc1.is_cuda else self.device
             pc1 = pc1.to(device=dev, dtype=torch.float32)              # generate_data.py:122 (stays on the GPU)
             with torch.cuda.device(dev):
-                return pc1, self._build(L, pc1, dev)
+                try:
+                    return pc1, self._build(L, pc1, dev, self.exact)
+                except VertexCapExceeded:
+                    # sparse cloud: more vertices than vertex_cap_factor * N; redo with per-level sizing
+                    return pc1, self._build(L, pc1, dev, True)
 
-    def _build(self, L, pc1, dev):
+    def _build(self, L, pc1, dev, exact):
         stream = _capi.stream_ptr()
         nlev = len(self.scales_filter_map)
         states = torch.empty((nlev, STATE_WORDS), dtype=torch.int32, device=dev)
@@ -117,14 +125,14 @@ class GenerateData(object):
             F = self.get_filter_size(radius) if radius != -1 else 0
             st = states[li]
             ws = self._ws(n, dev)
-            h_cap = 4 * n if self.exact else int(min(4 * n, max(self.vertex_cap_factor * n0, 1024)))
+            h_cap = 4 * n if exact else int(min(4 * n, max(self.vertex_cap_factor * n0, 1024)))
             bary = torch.empty((1, self.d1, n), dtype=torch.float32, device=dev)
             elmgr = torch.empty((1, self.d1, n), dtype=torch.float32, device=dev)
             _capi.check(L.efgh_lattice_points(pts.data_ptr(), max(pts.stride(0), n, 1), n, _capi.ptr(n_dev),
                                               float(scale), bary.data_ptr(), elmgr.data_ptr(), max(n, 1), h_cap,
                                               st.data_ptr(), ws.data_ptr(), ws.numel(), stream),
                         "efgh_lattice_points")
-            if self.exact:
+            if exact:
                 st_host = st.cpu()                                    # per-level sync: pc1_hash_cnt is a Python int
                 check_status(int(st_host[2]), li)
                 H = int(st_host[1])
@@ -149,10 +157,12 @@ class GenerateData(object):
             if has_next:
                 pts = nxt
                 n = h_alloc
-                n_dev = None if self.exact else st[1:2]
-        if not self.exact:
+                n_dev = None if exact else st[1:2]
+        if not exact:
             host = states.cpu()                                       # the only sync of the scan
             n_true = n0
+            if any(int(host[li, 2]) & 2 for li in range(nlev)):
+                raise VertexCapExceeded()
             for li, d in enumerate(out):
                 check_status(int(host[li, 2]), li)
                 H = int(host[li, 1])

@@ -1,0 +1,206 @@
+"""ScanPipeline - whole-scan forward (lattice build + all BCL layers) enqueued without a host round trip.
+
+This is the path BASELINE.json's metric is measured on: for one LiDAR scan it does what
+reference nets/enet.py:107-141 does between `generate_data(pc)` and `bcn5(...)` - the five-level lattice
+build (reference nets/generate_data.py:117-193) followed by the five BilateralConvFlex layers, each fed
+`cat(el_minus_gr_l, previous output)` - but
+
+  * every buffer is pre-allocated at capacity and every count (points per level, vertices per level) stays
+    in device memory, so the ~60 kernels of a scan are enqueued back to back on one stream;
+  * the `torch.cat` of reference enet.py:113-137 is never materialised: el_minus_gr and the previous
+    level's output are splatted into column ranges of the same vertex-major matrix;
+  * level l's output (vertex-major) IS level l+1's point-major feature matrix, so nothing is transposed;
+  * the reference-format int64 tensors (pc1_lattice_offset, pc1_blur_neighbors) are still produced - they
+    are part of the lattice build's contract - next to int32 copies that the BCL kernels read.
+
+Several pipelines on different CUDA streams run concurrently (one scan each); scans are independent
+(SURVEY.md §8e), which is also how they shard across GPUs.
+"""
+import numpy as np
+import torch
+
+from . import _capi
+from .generate_data import GenerateData, STATE_WORDS, check_status, VertexCapExceeded
+
+_ACT = {"none": 0, "relu": 1, "leaky": 2}
+
+
+class ScanPipeline(object):
+    def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
+                 vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True):
+        """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
+        weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
+        vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points."""
+        self.dev = torch.device(device)
+        self.L = _capi.lib()
+        self.n0 = int(n_points)
+        self.smap = scales_filter_map
+        self.plan = bcl_plan
+        self.nlev = len(scales_filter_map)
+        assert len(bcl_plan) == self.nlev and len(weights) == self.nlev
+        self.emit_int64 = emit_int64
+        self.final_act = 0 if not last_relu else (_ACT["leaky"] if use_leaky else _ACT["relu"])
+        self.use_norm = use_norm
+        self.gd = GenerateData(3, scales_filter_map, "cuda")
+        dev = self.dev
+        f32, i32, i64 = torch.float32, torch.int32, torch.int64
+        cap = max(int(vertex_cap_factor * self.n0), 1024)
+        self.levels = []
+        n_cap = self.n0
+        prev_c = stem_channels
+        with torch.cuda.device(dev):
+            self.states = torch.zeros((self.nlev, STATE_WORDS), dtype=i32, device=dev)
+            ws_bytes = 0
+            for li, (scale, radius) in enumerate(scales_filter_map):
+                cin, (cmid, cout) = bcl_plan[li]
+                assert cin == prev_c + 4, "level %d: C_in must be 4 + previous C_out" % li
+                assert radius != -1, "ScanPipeline needs a blur radius on every level"
+                F = self.gd.get_filter_size(radius)
+                h_cap = min(4 * n_cap, cap)
+                lv = {
+                    "n_cap": n_cap, "h_cap": h_cap, "F": F, "scale": float(scale), "cin": cin, "cmid": cmid, "cout": cout,
+                    "divisor": float(np.float32(self.gd.expected_std * scale)),
+                    "offs": torch.from_numpy(self.gd.radius2offset[radius].astype(np.int32)).to(dev),
+                    "bary": torch.empty((4, n_cap), dtype=f32, device=dev),
+                    "elmgr": torch.empty((4, n_cap), dtype=f32, device=dev),
+                    "loff32": torch.empty((4, n_cap), dtype=i32, device=dev),
+                    "nbr32": torch.empty((F, h_cap), dtype=i32, device=dev),
+                    "loff64": torch.empty((4, n_cap), dtype=i64, device=dev) if emit_int64 else None,
+                    "nbr64": torch.empty((F, h_cap), dtype=i64, device=dev) if emit_int64 else None,
+                    "next": torch.empty((3, h_cap), dtype=f32, device=dev) if li != self.nlev - 1 else None,
+                    "S": torch.empty((h_cap + 1, cin), dtype=f32, device=dev),
+                    "wsum": torch.empty((h_cap + 1,), dtype=f32, device=dev),
+                    "inv": torch.empty((h_cap + 1,), dtype=f32, device=dev),
+                    "Y": torch.empty((h_cap, cmid), dtype=f32, device=dev),
+                    "Z": torch.empty((h_cap, cout), dtype=f32, device=dev),
+                }
+                (W0, b0), (W1, b1) = weights[li]
+                M0, C0, F0, _ = W0.shape
+                assert (M0, C0, F0) == (cmid, cin, F)
+                lv["Wt0"] = W0.detach().to(dev, f32)[:, :, :, 0].permute(2, 1, 0).reshape(F * cin, cmid).contiguous()
+                lv["b0"] = b0.detach().to(dev, f32).contiguous()
+                lv["Wt1"] = W1.detach().to(dev, f32)[:, :, 0, 0].t().contiguous()
+                lv["b1"] = b1.detach().to(dev, f32).contiguous()
+                ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
+                self.levels.append(lv)
+                n_cap = h_cap
+                prev_c = cout
+            self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 2 + 1 + 2)
+
+    # ------------------------------------------------------------------------------------------
+    def enqueue(self, pc, feat0, stream=None, timers=None):
+        """pc (3,N) f32, feat0 (C_stem,N) f32 device tensors.  Enqueues the whole scan on `stream` (default:
+        current).  Returns the last level's output buffer Z (h_cap, C_out) - valid rows = states[-1, 1].
+        timers: optional dict name -> [(start_event, end_event), ...] to time individual stages."""
+        L, ck = self.L, _capi.check
+        s = (stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.dev).cuda_stream)
+        assert pc.shape[-1] == self.n0 and pc.stride(-1) == 1 and feat0.stride(-1) == 1
+        ws, wsn = self.ws.data_ptr(), self.ws.numel()
+
+        def timed(name, fn):
+            if timers is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+            a.record(st)
+            fn()
+            b.record(st)
+            timers.setdefault(name, []).append((a, b))
+
+        pts_ptr, pts_ld = pc.data_ptr(), pc.stride(0)
+        prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
+        n_dev = None
+        for li, lv in enumerate(self.levels):
+            st = self.states[li].data_ptr()
+            n_cap, h_cap, cin = lv["n_cap"], lv["h_cap"], lv["cin"]
+            h_dev = st + 4           # &state.hash_cnt
+            timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points(
+                pts_ptr, pts_ld, n_cap, n_dev, lv["scale"], lv["bary"].data_ptr(), lv["elmgr"].data_ptr(), n_cap, h_cap,
+                st, ws, wsn, s), "efgh_lattice_points"))
+            timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices(
+                n_cap, _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap, lv["offs"].data_ptr(), lv["F"], h_cap,
+                _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
+                st, ws, wsn, s), "efgh_lattice_vertices"))
+            S = lv["S"].data_ptr()
+            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), h_cap + 1, h_dev, 1, s),
+                                              "efgh_bcl_zero"))
+
+            def splat():
+                ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, n_cap, n_dev, lv["bary"].data_ptr(), n_cap,
+                                      lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
+                                      lv["wsum"].data_ptr() if self.use_norm else None, s), "efgh_bcl_scatter")
+                ck(L.efgh_bcl_scatter(prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev, lv["bary"].data_ptr(), n_cap,
+                                      lv["loff32"].data_ptr(), 32, n_cap, 1, S + 16, cin, None, s), "efgh_bcl_scatter")
+                if self.use_norm:
+                    ck(L.efgh_bcl_inv_norm(lv["wsum"].data_ptr(), lv["inv"].data_ptr(), h_cap + 1, h_dev, 1, s),
+                       "efgh_bcl_inv_norm")
+            timed("L%d.splat" % li, splat)
+            timed("L%d.conv1" % li, lambda: ck(L.efgh_bcl_conv(
+                S, cin, cin, lv["inv"].data_ptr() if self.use_norm else None, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"],
+                h_cap, h_dev, lv["Wt0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
+                lv["cmid"], 0, s), "efgh_bcl_conv"))
+            timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv(
+                lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, None, 32, 0, 1, h_cap, h_dev, lv["Wt1"].data_ptr(),
+                lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(), lv["cout"], 0, s), "efgh_bcl_conv"))
+            if lv["next"] is not None:
+                pts_ptr, pts_ld = lv["next"].data_ptr(), h_cap
+            prev_ptr, prev_sc, prev_sn, prev_c = lv["Z"].data_ptr(), 1, lv["cout"], lv["cout"]
+            n_dev = h_dev
+        return self.levels[-1]["Z"]
+
+    def counts(self):
+        """Synchronising read of the per-level records: returns [H_0..H_4]; raises on a status bit."""
+        host = self.states.cpu()
+        for li in range(self.nlev):
+            if int(host[li, 2]) & 2:
+                raise VertexCapExceeded("level %d: more vertices than vertex_cap_factor * N allows" % li)
+            check_status(int(host[li, 2]), li)
+        return [int(host[li, 1]) for li in range(self.nlev)]
+
+    def level_dicts(self):
+        """The reference-format per-level dicts (views of the pipeline's buffers) of the last scan."""
+        cnt = self.counts()
+        out, n = [], self.n0
+        for li, lv in enumerate(self.levels):
+            H = cnt[li]
+            out.append({"pc1_barycentric": lv["bary"][None, :, :n], "pc1_el_minus_gr": lv["elmgr"][None, :, :n],
+                        "pc1_lattice_offset": (lv["loff64"] if self.emit_int64 else lv["loff32"])[None, :, :n],
+                        "pc1_blur_neighbors": (lv["nbr64"] if self.emit_int64 else lv["nbr32"])[None, :, :H],
+                        "pc1_hash_cnt": H})
+            n = H
+        return out
+
+    def outputs(self):
+        """[(1, C_out, H_l) views] - what bcn1..bcn5 return in reference enet.py:113-141."""
+        cnt = self.counts()
+        return [lv["Z"][:cnt[li]].t()[None] for li, lv in enumerate(self.levels)]
+
+    # ------------------------------------------------------------------------------------------
+    def algorithmic_bytes(self, counts):
+        """SURVEY.md §8(d) per-level byte model, summed: lattice 76 N + 132 H;
+        BCL fwd 4 C_in N + 48 N + 8 C_in (H+1) + 120 H + 4 C_out H."""
+        total, per_level, n = 0, [], self.n0
+        for li, lv in enumerate(self.levels):
+            H = counts[li]
+            lat = 76 * n + 132 * H
+            bcl = 4 * lv["cin"] * n + 48 * n + 8 * lv["cin"] * (H + 1) + 120 * H + 4 * lv["cout"] * H
+            per_level.append((lat, bcl))
+            total += lat + bcl
+            n = H
+        return total, per_level
+
+    def conv_flops(self, counts):
+        """2 * H * (F*C_in*C_mid + C_mid*C_out) per level."""
+        return [2 * counts[li] * (lv["F"] * lv["cin"] * lv["cmid"] + lv["cmid"] * lv["cout"])
+                for li, lv in enumerate(self.levels)]
+
+
+def make_enet_weights(bcl_plan, filter_size=15, std=0.1, seed=0):
+    """Random-init BCL weights with the reference's shapes (nets/bilateralNN.py:103-135)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for cin, (cmid, cout) in bcl_plan:
+        out.append([(torch.randn(cmid, cin, filter_size, 1, generator=g) * std, torch.randn(cmid, generator=g) * std),
+                    (torch.randn(cout, cmid, 1, 1, generator=g) * std, torch.randn(cout, generator=g) * std)])
+    return out

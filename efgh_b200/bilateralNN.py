@@ -14,6 +14,8 @@ Only batch size 1 is meaningful in the reference (bilateralNN.py:162-165: "batch
 for now"; the splat indices carry no batch offset), so B != 1 raises here instead of silently mixing
 the batch entries.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -22,6 +24,13 @@ from . import _capi
 DELETE_TMP_VARIABLES = False
 
 _ACT = {"none": 0, "relu": 1, "leaky": 2}
+
+# Arithmetic of the lattice convolution's contraction (forward):
+#   "3xtf32" tcgen05 tensor cores with 3xTF32 operand splitting - fp32-equivalent, the default;
+#   "tf32"   tcgen05, one TF32 pass - what cuDNN gives the reference under torch's default allow_tf32;
+#   "fp32"   CUDA-core FFMA kernel (also the automatic choice for shapes the tensor-core kernel rejects).
+CONV_PRECISION = os.environ.get("EFGH_CONV_PRECISION", "3xtf32")
+_NSPLIT = {"3xtf32": 3, "tf32": 1}
 
 
 def init_weights(m):
@@ -98,9 +107,26 @@ def conv(X, row_scale, nbr, Wt, bias, act, h):
         F, bits, nbp = nb2.shape[0], _idx_bits(nb2), nb2.data_ptr()
     else:
         F, bits, nbp, nb_ld = 1, 64, None, 0
-    _capi.check(_capi.lib().efgh_bcl_conv(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F, h,
-                                          None, Wt.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, 0,
-                                          _capi.stream_ptr()), "efgh_bcl_conv")
+    L = _capi.lib()
+    nsplit = _NSPLIT.get(CONV_PRECISION, 0)
+    if nsplit and L.efgh_bcl_conv_tc_supported(C, F, M, nsplit) and X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0:
+        K = Wt.shape[0]
+        img = torch.empty(L.efgh_bcl_packed_weight_bytes(K, M, nsplit) // 4, dtype=torch.float32, device=X.device)
+        _capi.check(L.efgh_bcl_pack_weights(Wt.data_ptr(), K, M, nsplit, img.data_ptr(), _capi.stream_ptr()),
+                    "efgh_bcl_pack_weights")
+        split = L.efgh_bcl_conv_tc_groups(K) > 1        # long contraction: partial sums are added in L2
+        if split:
+            Y.zero_()
+        _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), None, 0, nbp, bits, nb_ld, F, h,
+                                       None, img.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, nsplit,
+                                       1 if split else 0, _capi.stream_ptr()), "efgh_bcl_conv_tc")
+        if split:
+            _capi.check(L.efgh_bcl_bias_act(Y.data_ptr(), M, M, h, None, _capi.ptr(bias), act, _capi.stream_ptr()),
+                        "efgh_bcl_bias_act")
+        return Y
+    _capi.check(L.efgh_bcl_conv(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F, h,
+                                None, Wt.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, 0,
+                                _capi.stream_ptr()), "efgh_bcl_conv")
     return Y
 
 

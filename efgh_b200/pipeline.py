@@ -27,10 +27,12 @@ _ACT = {"none": 0, "relu": 1, "leaky": 2}
 
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
-                 vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True):
+                 vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
+                 precision="3xtf32"):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
-        vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points."""
+        vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
+        precision: "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05, one pass) or "fp32" (CUDA cores)."""
         self.dev = torch.device(device)
         self.L = _capi.lib()
         self.n0 = int(n_points)
@@ -41,6 +43,8 @@ class ScanPipeline(object):
         self.emit_int64 = emit_int64
         self.final_act = 0 if not last_relu else (_ACT["leaky"] if use_leaky else _ACT["relu"])
         self.use_norm = use_norm
+        self.precision = precision
+        self.nsplit = {"3xtf32": 3, "tf32": 1, "fp32": 0}[precision]
         self.gd = GenerateData(3, scales_filter_map, "cuda")
         dev = self.dev
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
@@ -81,25 +85,38 @@ class ScanPipeline(object):
                 lv["b0"] = b0.detach().to(dev, f32).contiguous()
                 lv["Wt1"] = W1.detach().to(dev, f32)[:, :, 0, 0].t().contiguous()
                 lv["b1"] = b1.detach().to(dev, f32).contiguous()
+                lv["tc"] = bool(self.nsplit and self.L.efgh_bcl_conv_tc_supported(cin, F, cmid, self.nsplit)
+                                and self.L.efgh_bcl_conv_tc_supported(cmid, 1, cout, self.nsplit)
+                                and self.L.efgh_bcl_conv_tc_groups(cmid) == 1)
+                if lv["tc"]:
+                    for nm, K, M in (("img0", F * cin, cmid), ("img1", cmid, cout)):
+                        img = torch.empty(self.L.efgh_bcl_packed_weight_bytes(K, M, self.nsplit) // 4, dtype=f32, device=dev)
+                        _capi.check(self.L.efgh_bcl_pack_weights(lv["Wt" + nm[-1]].data_ptr(), K, M, self.nsplit, img.data_ptr(),
+                                                                 torch.cuda.current_stream(dev).cuda_stream), "efgh_bcl_pack_weights")
+                        lv[nm] = img
+                    lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin) > 1
                 ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
                 self.levels.append(lv)
                 n_cap = h_cap
                 prev_c = cout
             self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 2 + 1 + 2)
+            self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
+            self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
+        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 2 + 1 + 2) + sum(1 for lv in self.levels if lv.get("split0"))
 
     # ------------------------------------------------------------------------------------------
     def enqueue(self, pc, feat0, stream=None, timers=None):
         """pc (3,N) f32, feat0 (C_stem,N) f32 device tensors.  Enqueues the whole scan on `stream` (default:
         current).  Returns the last level's output buffer Z (h_cap, C_out) - valid rows = states[-1, 1].
-        timers: optional dict name -> [(start_event, end_event), ...] to time individual stages."""
+        timers: optional dict; stages whose name is a key (or every stage if "*" is a key) get a CUDA event
+        pair appended to timers[name]."""
         L, ck = self.L, _capi.check
         s = (stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.dev).cuda_stream)
         assert pc.shape[-1] == self.n0 and pc.stride(-1) == 1 and feat0.stride(-1) == 1
         ws, wsn = self.ws.data_ptr(), self.ws.numel()
 
         def timed(name, fn):
-            if timers is None:
+            if timers is None or not (name in timers or "*" in timers):
                 return fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             st = stream if stream is not None else torch.cuda.current_stream(self.dev)
@@ -136,18 +153,49 @@ class ScanPipeline(object):
                     ck(L.efgh_bcl_inv_norm(lv["wsum"].data_ptr(), lv["inv"].data_ptr(), h_cap + 1, h_dev, 1, s),
                        "efgh_bcl_inv_norm")
             timed("L%d.splat" % li, splat)
-            timed("L%d.conv1" % li, lambda: ck(L.efgh_bcl_conv(
-                S, cin, cin, lv["inv"].data_ptr() if self.use_norm else None, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"],
-                h_cap, h_dev, lv["Wt0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
-                lv["cmid"], 0, s), "efgh_bcl_conv"))
-            timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv(
-                lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, None, 32, 0, 1, h_cap, h_dev, lv["Wt1"].data_ptr(),
-                lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(), lv["cout"], 0, s), "efgh_bcl_conv"))
+            inv_ptr = lv["inv"].data_ptr() if self.use_norm else None
+            if lv["tc"]:
+                # conv1 on tensor cores: long contraction -> partial sums added in L2, bias + ReLU deferred to
+                # conv2's loader (in_bias / in_act), so Y holds raw sums and is never re-written
+                split = lv["split0"]
+
+                def conv1():
+                    if split:
+                        ck(L.efgh_bcl_zero(lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, h_cap, h_dev, 0, s), "efgh_bcl_zero")
+                    ck(L.efgh_bcl_conv_tc(S, cin, cin, inv_ptr, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"], h_cap, h_dev,
+                                          lv["img0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
+                                          lv["cmid"], self.nsplit, 1 if split else 0, s), "efgh_bcl_conv_tc")
+                timed("L%d.conv1" % li, conv1)
+                timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv_tc(
+                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, lv["b0"].data_ptr() if split else None, _ACT["relu"], None, 32, 0,
+                    1, h_cap, h_dev, lv["img1"].data_ptr(), lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(),
+                    lv["cout"], self.nsplit, 0, s), "efgh_bcl_conv_tc"))
+            else:
+                timed("L%d.conv1" % li, lambda: ck(L.efgh_bcl_conv(
+                    S, cin, cin, inv_ptr, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"],
+                    h_cap, h_dev, lv["Wt0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
+                    lv["cmid"], 0, s), "efgh_bcl_conv"))
+                timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv(
+                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, None, 32, 0, 1, h_cap, h_dev, lv["Wt1"].data_ptr(),
+                    lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(), lv["cout"], 0, s), "efgh_bcl_conv"))
             if lv["next"] is not None:
                 pts_ptr, pts_ld = lv["next"].data_ptr(), h_cap
             prev_ptr, prev_sc, prev_sn, prev_c = lv["Z"].data_ptr(), 1, lv["cout"], lv["cout"]
             n_dev = h_dev
         return self.levels[-1]["Z"]
+
+    def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None):
+        """End-to-end call on HOST buffers (pinned for async copies): H2D of the cloud and stem features,
+        the whole scan, D2H of the level records and of the first out_host.shape[0] rows of the last
+        level's output.  Everything is enqueued on `stream`; synchronise it before reading the outputs."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(st):
+            self._pc_dev.copy_(pc_host, non_blocking=True)
+            self._feat_dev.copy_(feat_host, non_blocking=True)
+            Z = self.enqueue(self._pc_dev, self._feat_dev, stream=st)
+            out_host.copy_(Z[:out_host.shape[0]], non_blocking=True)
+            state_host.copy_(self.states, non_blocking=True)
+        return out_host, state_host
 
     def counts(self):
         """Synchronising read of the per-level records: returns [H_0..H_4]; raises on a status bit."""

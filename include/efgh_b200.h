@@ -146,6 +146,35 @@ int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *row_scale, co
                   int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *Wt, const float *bias,
                   int M, int act, float *Y, int64_t ldY, int precision, void *stream);
 
+/* Tensor-core variant of efgh_bcl_conv (tcgen05 / TMEM, kind::tf32, fp32 accumulate).
+ *   nsplit = 3: 3xTF32 operand splitting, fp32-equivalent accuracy (parity tests hold 1e-5);
+ *   nsplit = 1: one TF32 pass (what cuDNN does for the reference under torch's default allow_tf32).
+ * Weights are passed PACKED: efgh_bcl_pack_weights turns the (F*C, M) row-major matrix that efgh_bcl_conv
+ * takes into the swizzled shared-memory image the kernel streams in with bulk copies (pack once per weight
+ * update; efgh_bcl_packed_weight_bytes gives the buffer size, 16-byte aligned).
+ * efgh_bcl_conv_tc_supported: 1 if the shape can run here (C % 4 == 0, M in {32,64,...,256}), else use
+ * efgh_bcl_conv.  X, Y 16-byte aligned, ldX and ldY multiples of 4.
+ *
+ * Long contractions are cut into efgh_bcl_conv_tc_groups(K) partial sums (tensor-core accumulation rounds
+ * toward zero, so chains are kept short; the cut is also the split-K that fills the GPU on small lattices).
+ *   accumulate = 0: Y = act(bias + sum); only valid when efgh_bcl_conv_tc_groups(F*C) == 1;
+ *   accumulate = 1: Y += partial sums (red.add in L2) - the caller zero-fills Y first; bias/act are NOT
+ *                   applied: finish with efgh_bcl_bias_act, or let the consumer apply them on load through
+ *                   its in_bias / in_act arguments.
+ *   in_bias (C floats) / in_act: optional transform of the INPUT, x = act(x + in_bias[c]), applied as rows are
+ *                   gathered - the deferred bias + ReLU of a producer that ran with accumulate = 1. */
+int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit);
+int efgh_bcl_conv_tc_groups(int K);
+size_t efgh_bcl_packed_weight_bytes(int K, int M, int nsplit);
+int efgh_bcl_pack_weights(const float *Wt, int K, int M, int nsplit, float *Wimg, void *stream);
+int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *row_scale, const float *in_bias, int in_act,
+                     const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev,
+                     const float *Wimg, const float *bias, int M, int act, float *Y, int64_t ldY, int nsplit,
+                     int accumulate, void *stream);
+/* Y[h, m] = act(Y[h, m] + bias[m]) in place, h < (h_dev ? *h_dev : h). */
+int efgh_bcl_bias_act(float *Y, int64_t ldY, int M, int64_t h, const int32_t *h_dev, const float *bias, int act,
+                      void *stream);
+
 /* Backward of efgh_bcl_conv w.r.t. its input: dX[nbr[f,h]+1, c] += sum_m dY[h,m] * Wt[(f*C+c), m]
  * (absent neighbours are skipped; nbr == NULL: dX[h, c] = ..., plain store).  If act_out != NULL the
  * incoming gradient is first masked by the forward activation: dY *= act'(act_out) where act_out is

@@ -77,10 +77,11 @@ def scatter(feat_cn, w, off, row_shift, rows, want_wsum):
     return S, wsum
 
 
-def inv_norm(wsum):
+def normalize_(S, wsum):
+    """S[r, :] *= 1/(wsum[r] + 1e-5) in place; returns the factors (needed by the backward pass)."""
     inv = torch.empty_like(wsum)
-    _capi.check(_capi.lib().efgh_bcl_inv_norm(wsum.data_ptr(), inv.data_ptr(), wsum.numel(), None, 0,
-                                              _capi.stream_ptr()), "efgh_bcl_inv_norm")
+    _capi.check(_capi.lib().efgh_bcl_normalize(S.data_ptr(), S.stride(0), S.shape[1], wsum.data_ptr(), inv.data_ptr(),
+                                               wsum.numel(), None, 0, _capi.stream_ptr()), "efgh_bcl_normalize")
     return inv
 
 
@@ -97,8 +98,8 @@ def gather(Z, row_scale, w, off, row_shift, bias, n):
     return out
 
 
-def conv(X, row_scale, nbr, Wt, bias, act, h):
-    """X (rows, C); nbr (1,F,h) or None; Wt (F*C, M) -> Y (h, M)."""
+def conv(X, nbr, Wt, bias, act, h):
+    """X (rows, C) (already normalised); nbr (1,F,h) or None; Wt (F*C, M) -> Y (h, M)."""
     C = X.shape[1]
     M = Wt.shape[1]
     Y = torch.empty((h, M), dtype=torch.float32, device=X.device)
@@ -117,14 +118,14 @@ def conv(X, row_scale, nbr, Wt, bias, act, h):
         split = L.efgh_bcl_conv_tc_groups(K) > 1        # long contraction: partial sums are added in L2
         if split:
             Y.zero_()
-        _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), None, 0, nbp, bits, nb_ld, F, h,
+        _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), X.stride(0), C, None, 0, nbp, bits, nb_ld, F, h,
                                        None, img.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, nsplit,
                                        1 if split else 0, _capi.stream_ptr()), "efgh_bcl_conv_tc")
         if split:
             _capi.check(L.efgh_bcl_bias_act(Y.data_ptr(), M, M, h, None, _capi.ptr(bias), act, _capi.stream_ptr()),
                         "efgh_bcl_bias_act")
         return Y
-    _capi.check(L.efgh_bcl_conv(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F, h,
+    _capi.check(L.efgh_bcl_conv(X.data_ptr(), X.stride(0), C, None, nbp, bits, nb_ld, F, h,
                                 None, Wt.data_ptr(), _capi.ptr(bias), M, act, Y.data_ptr(), M, 0,
                                 _capi.stream_ptr()), "efgh_bcl_conv")
     return Y
@@ -192,20 +193,20 @@ class _BCLFunction(torch.autograd.Function):
             if do_splat:
                 S, wsum = scatter(feat, in_bary, in_off, 1, H + 1, use_norm)
                 if use_norm:
-                    inv = inv_norm(wsum)
+                    inv = normalize_(S, wsum)      # S now holds the normalised splat (bilateralNN.py:210-211)
             else:
                 S = torch.zeros((H + 1, feat.shape[0]), dtype=torch.float32, device=feat.device)
                 S[1:] = feat.t()
             nconv = len(wb) // 2
             xs, ys, wts, acts = [], [], [], []
-            X, rs, nb = S, inv, nbr
+            X, nb = S, nbr
             for k in range(nconv):
                 W, b = wb[2 * k], wb[2 * k + 1]
                 Wt = _wt_first(W) if k == 0 else _wt_point(W)
                 act = _ACT["relu"] if k < nconv - 1 else final_act
-                Y = conv(X, rs, nb, Wt, b, act, H)
+                Y = conv(X, nb, Wt, b, act, H)
                 xs.append(X); ys.append(Y); wts.append(Wt); acts.append(act)
-                X, rs, nb = Y, None, None
+                X, nb = Y, None
             if do_slice:
                 n_out = out_bary.shape[-1]
                 out = gather(X, None, out_bary, out_off, 0, slice_bias, n_out)[None]
@@ -249,7 +250,7 @@ class _BCLFunction(torch.autograd.Function):
                 need_w = ctx.needs_input_grad[8 + 2 * k]
                 need_b = ctx.needs_input_grad[8 + 2 * k + 1]
                 if need_w or need_b:
-                    dWt, db = conv_wgrad(X, inv if first else None, nbr if first else None, dY, act_out, act, need_b)
+                    dWt, db = conv_wgrad(X, None, nbr if first else None, dY, act_out, act, need_b)
                     if need_w:
                         if first:
                             F = nbr.shape[1]

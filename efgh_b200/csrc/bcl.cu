@@ -98,6 +98,35 @@ __global__ void k_zero(float *__restrict__ S, int64_t ldS, int C, float *__restr
     for (int64_t i = tid; i < rows; i += stride) wsum[i] = 0.f;
 }
 
+__global__ void k_normalize(float *__restrict__ S, int64_t ldS, int C, const float *__restrict__ wsum,
+                            float *__restrict__ inv_out, int rows_host, const int32_t *rows_dev, int rows_extra) {
+  const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
+  const int C4 = C / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (C % 4 == 0 && ldS % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
+    const int64_t total = (int64_t)rows * C4;
+    for (int64_t i = tid; i < total; i += stride) {
+      const int64_t row = i / C4;
+      const int c4 = (int)(i - row * C4);
+      const float inv = __fdiv_rn(1.0f, __fadd_rn(__ldg(wsum + row), 1e-5f));
+      float4 *q = reinterpret_cast<float4 *>(S + row * ldS) + c4;
+      float4 v = *q;
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      *q = v;
+      if (inv_out && c4 == 0) inv_out[row] = inv;
+    }
+  } else {
+    const int64_t total = (int64_t)rows * C;
+    for (int64_t i = tid; i < total; i += stride) {
+      const int64_t row = i / C;
+      const int c = (int)(i - row * C);
+      const float inv = __fdiv_rn(1.0f, __fadd_rn(__ldg(wsum + row), 1e-5f));
+      S[row * ldS + c] *= inv;
+      if (inv_out && c == 0) inv_out[row] = inv;
+    }
+  }
+}
+
 __global__ void k_inv_norm(const float *__restrict__ wsum, float *__restrict__ inv, int rows_host,
                            const int32_t *rows_dev, int rows_extra) {
   const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
@@ -483,6 +512,17 @@ extern "C" int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, int64_t 
   EFGH_REQUIRE(S, "efgh_bcl_zero: null pointer");
   k_zero<<<grid_for(rows_cap * C / 4, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ldS, C, wsum, (int)rows_cap,
                                                                                          rows_dev, rows_extra);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
+}
+
+extern "C" int efgh_bcl_normalize(float *S, int64_t ldS, int C, const float *wsum, float *inv_out, int64_t rows,
+                                  const int32_t *rows_dev, int rows_extra, void *stream) {
+  EFGH_REQUIRE(C > 0 && ldS >= C && rows >= 0 && rows < (1ll << 31), "efgh_bcl_normalize: bad sizes");
+  if (rows == 0) return EFGH_OK;
+  EFGH_REQUIRE(S && wsum, "efgh_bcl_normalize: null pointer");
+  k_normalize<<<grid_for(rows * C / 4, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ldS, C, wsum, inv_out, (int)rows,
+                                                                                          rows_dev, rows_extra);
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
 }

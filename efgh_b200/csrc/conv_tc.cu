@@ -5,10 +5,10 @@
 // reference nets/bilateralNN.py:240-244: advanced-index gather that materialises (1, C, F, H), then a cuDNN
 // (F,1) convolution.  Here the gather IS the A-operand loader of a warp-specialised GEMM:
 //
-//   warps 0-7   gather producers: thread -> (tile row, half of a 32-float K chunk); reads 16-byte pieces of
-//               neighbour rows from the vertex-major splat matrix (L2), applies the density normalisation,
-//               splits every value into a TF32-exact "big" part and the fp32 remainder "small", and stores
-//               both into 128-byte-swizzled K-major shared-memory tiles (the UMMA canonical layout)
+//   warps 0-7   gather producers, two teams of 128 (thread = tile row): cp.async 16-byte pieces of neighbour
+//               rows of the (already normalised) vertex-major splat matrix from L2 straight into the
+//               128-byte-swizzled K-major A tile (the UMMA canonical layout), several chunks in flight; then
+//               split each landed value in place into a TF32-exact "big" part and the fp32 remainder "small"
 //   warp  8     MMA issuer: one thread issues tcgen05.mma kind::tf32, M=128 x N x K=8, accumulators in TMEM.
 //               3xTF32: D += A_small*B_big + A_big*B_small + A_big*B_big  (fp32-equivalent accuracy; the
 //               dropped small*small term is 2^-22 relative), or a single TF32 pass when nsplit == 1
@@ -20,6 +20,11 @@
 // tile t+1; a ring of shared-memory stages (full/empty mbarriers) decouples gather, weight load and MMA.
 // Persistent CTAs, one per SM, stride over 128-vertex tiles; the vertex count is read from device memory.
 #include "common.cuh"
+
+static unsigned long long *g_conv_trace = nullptr;
+// Debug hook (not part of the public header): device buffer of 5 roles x 512 x 2 u64 that CTA 0 fills with
+// (event, globaltimer) pairs, or NULL to disable.
+extern "C" void efgh_debug_set_conv_trace(unsigned long long *buf) { g_conv_trace = buf; }
 
 namespace efgh {
 namespace {
@@ -113,9 +118,21 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
+// Optional timeline trace (debug): role r of CTA 0 appends (event, globaltimer) pairs to trace[r*kTraceCap...]
+constexpr int kTraceCap = 512;
+__device__ __forceinline__ void trace_ev(unsigned long long *trace, int role, int &n, int ev) {
+  if (trace && blockIdx.x == 0 && n < kTraceCap) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)role * kTraceCap * 2 + 2 * n] = (unsigned long long)ev;
+    trace[(size_t)role * kTraceCap * 2 + 2 * n + 1] = t;
+    ++n;
+  }
+}
+
 struct ConvParams {
+  unsigned long long *trace;
   const float *X; int64_t ldX; int C;
-  const float *row_scale;
   const float *in_bias; int in_act;     // optional input transform x = act(x + in_bias[c]) (deferred epilogue of a split-K producer)
   const void *nbr; int64_t nbr_ld; int F;
   int h_host; const int32_t *h_dev;
@@ -135,16 +152,14 @@ __device__ __forceinline__ void group_range(int n_chunks, int n_groups, int g, i
 template <typename IdxT, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A_big | A_small? | B_big | B_small?)] [row table F x 128 int] [scale table F x 128 f32] [barriers]
+  // carve: [stages x (A_big | A_small? | B_big | B_small?)] [barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int N = p.N;
   const uint32_t a_bytes = kABytes * (NSPLIT == 3 ? 2 : 1);
   const uint32_t b_bytes = (uint32_t)N * 128u * (NSPLIT == 3 ? 2 : 1);
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  int *s_rows = reinterpret_cast<int *>(smem + (size_t)p.stages * stage_bytes);
-  float *s_scl = reinterpret_cast<float *>(s_rows + p.F * kTileM);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_scl + p.F * kTileM);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages,
                  bar_acc_full = bar_empty + 8 * kMaxStages, bar_acc_empty = bar_acc_full + 16;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, kProducerThreads + 1);
+      mbar_init(bar_full + 8 * s, 128 + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -177,62 +192,77 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
 
   if (warp < kProducerWarps) {
     // ===================== gather producers =====================
-    const int r = threadIdx.x & (kTileM - 1), half = threadIdx.x >> 7;
+    // Two teams of 128 threads (thread = tile row) alternate over this CTA's work items, so one team's
+    // pipeline drain / neighbour-table load overlaps the other team's copies.  Per K chunk a thread
+    //   1. cp.async's (LDGSTS, zero-fill for absent neighbours) the 8 x 16-byte pieces of its row straight
+    //      from the vertex-major matrix into the swizzled A tile - up to `depth` chunks in flight, no
+    //      registers held across the L2 latency,
+    //   2. once its own copies have landed, re-reads them, applies the optional deferred bias + activation,
+    //      splits every value into the TF32-exact "big" part (written back in place) and the fp32 remainder
+    //      "small" (second tile), fences the generic->async proxy and arrives on the stage's full barrier.
+    const int team = warp >> 2;
+    const int r = threadIdx.x & (kTileM - 1);
     const uint32_t swz = (uint32_t)(r & 7);
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int depth = min(4, p.stages - 1);
+    uint32_t it = 0;       // global chunk sequence number of this CTA (both teams track all items)
+    int k_item = 0, ntrace = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k_item) {
       const int tile = item / p.n_groups, grp = item - tile * p.n_groups;
       int j_begin, j_end;
       group_range(p.n_chunks, p.n_groups, grp, j_begin, j_end);
-      const int h0 = tile * kTileM;
-      const int f_lo = (j_begin * kChunkK) / p.C, f_hi = min(p.F - 1, (j_end * kChunkK - 1) / p.C);
-      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // previous item's table fully consumed
-      for (int idx = f_lo * kTileM + threadIdx.x; idx < (f_hi + 1) * kTileM; idx += kProducerThreads) {
-        const int f = idx / kTileM, rr = idx - f * kTileM;
-        int row = -1;
-        if (h0 + rr < H) row = p.nbr ? load_idx<IdxT>(p.nbr, f * p.nbr_ld + h0 + rr) + 1 : h0 + rr;
-        if (p.nbr && row == 0) row = -1;                                     // sink row: all zeros
-        s_rows[idx] = row;
-        s_scl[idx] = (row >= 0 && p.row_scale) ? __ldg(p.row_scale + row) : 1.0f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+      if ((k_item & 1) != team) { it += (uint32_t)(j_end - j_begin); continue; }
+      const int h = tile * kTileM + r;
+      const bool has_next = item + (int)gridDim.x < n_items;
+      // Neighbour rows of this thread's vertex for filter taps f, f+1, f+2 live in registers and are refilled
+      // two taps ahead of use (coalesced 512-byte reads across the team), so no index table / barrier is needed.
+      int f_cur = (j_begin * kChunkK) / p.C;
+      int c_cur = j_begin * kChunkK - f_cur * p.C;
+      auto fetch_row = [&](int f) -> int {
+        if (h >= H || f >= p.F) return -1;
+        if (!p.nbr) return h;
+        const int row = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h) + 1;
+        return row == 0 ? -1 : row;                                          // sink row: all zeros
+      };
+      int row0 = fetch_row(f_cur), row1 = fetch_row(f_cur + 1), row2 = fetch_row(f_cur + 2);
+      // Stage slots are claimed in global chunk order: this team may start claiming only after the other team
+      // has claimed every slot of the previous item (mbarrier parity cannot tell phases two apart).
+      if (k_item > 0) asm volatile("bar.sync %0, 256;" ::"r"(3 + (team ^ 1)) : "memory");
+      bool handed_off = false;
 
-      float4 cur[4], nxt[4];
-      float scl_cur[4], scl_nxt[4];
-      auto load_chunk = [&](int j, float4 *v, float *sc) {
+      auto issue = [&](int j, uint32_t seq) {
+        const uint32_t s = seq % p.stages, ph = (seq / p.stages) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t a_big = smem_base + s * stage_bytes + (uint32_t)r * 128u;
+        int k = j * kChunkK;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = j * kChunkK + (half * 4 + q) * 4;
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          sc[q] = 1.0f;
-          if (k < K) {
-            const int f = k / p.C, c = k - f * p.C;
-            const int row = s_rows[f * kTileM + r];
-            if (row >= 0) {
-              v[q] = __ldg(reinterpret_cast<const float4 *>(p.X + (int64_t)row * p.ldX + c));
-              sc[q] = s_scl[f * kTileM + r];
-              if (p.in_bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.in_bias + c));
-                v[q].x = act_apply(v[q].x + b.x, p.in_act); v[q].y = act_apply(v[q].y + b.y, p.in_act);
-                v[q].z = act_apply(v[q].z + b.z, p.in_act); v[q].w = act_apply(v[q].w + b.w, p.in_act);
-              }
-            }
+        for (int u = 0; u < 8; ++u) {
+          const int row = k < K ? row0 : -1;
+          const float *src = row >= 0 ? p.X + (int64_t)row * p.ldX + c_cur : p.X;
+          const uint32_t nbytes = row >= 0 ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_big + (((uint32_t)u ^ swz) << 4)), "l"(src), "r"(nbytes)
+                       : "memory");
+          k += 4; c_cur += 4;
+          if (c_cur >= p.C) {
+            c_cur = 0; ++f_cur;
+            row0 = row1; row1 = row2; row2 = fetch_row(f_cur + 2);
           }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      load_chunk(j_begin, cur, scl_cur);
-      for (int j = j_begin; j < j_end; ++j, ++it) {
-        if (j + 1 < j_end) load_chunk(j + 1, nxt, scl_nxt);
-        const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t a_big = smem_base + s * stage_bytes, a_small = a_big + kABytes;
+      auto convert = [&](int j, uint32_t seq) {
+        const uint32_t s = seq % p.stages;
+        const uint32_t a_big = smem_base + s * stage_bytes + (uint32_t)r * 128u, a_small = a_big + kABytes;
+        int c = (j * kChunkK) % p.C;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t u = (uint32_t)(half * 4 + q);
-          const uint32_t off = (uint32_t)r * 128u + ((u ^ swz) << 4);
-          float4 v = cur[q];
-          const float sc = scl_cur[q];
-          v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t off = ((uint32_t)u ^ swz) << 4;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_big + off) : "memory");
+          if (p.in_bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.in_bias + c));
+            v.x = act_apply(v.x + b.x, p.in_act); v.y = act_apply(v.y + b.y, p.in_act);
+            v.z = act_apply(v.z + b.z, p.in_act); v.w = act_apply(v.w + b.w, p.in_act);
+          }
           float4 big;
           big.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
           big.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -244,23 +274,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
                          "f"(v.z - big.z), "f"(v.w - big.w)
                          : "memory");
           }
+          c += 4;
+          if (c >= p.C) c = 0;
         }
         fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { cur[q] = nxt[q]; scl_cur[q] = scl_nxt[q]; }
+      };
+
+      int ji = j_begin, jc = j_begin;
+      const bool tracer = (threadIdx.x & 127) == 0;
+      if (tracer) trace_ev(p.trace, team, ntrace, 100 + k_item);
+      while (jc < j_end) {
+        while (ji < j_end && ji - jc < depth) {
+          issue(ji, it + (uint32_t)(ji - j_begin)); ++ji;
+          if (tracer) trace_ev(p.trace, team, ntrace, 1);
+        }
+        if (ji == j_end && !handed_off) {
+          handed_off = true;
+          if (has_next) asm volatile("bar.arrive %0, 256;" ::"r"(3 + team) : "memory");
+        }
+        const int pending = ji - jc - 1;         // younger groups that may still be in flight
+        if (pending >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tracer) trace_ev(p.trace, team, ntrace, 2);
+        convert(jc, it + (uint32_t)(jc - j_begin));
+        if (tracer) trace_ev(p.trace, team, ntrace, 3);
+        ++jc;
       }
+      it += (uint32_t)(j_end - j_begin);
     }
   } else if (warp == kTmaWarp) {
     // ===================== weight loader (TMA bulk copies) =====================
     if (lane == 0) {
       uint32_t it = 0;
+      int ntrace = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int j_begin, j_end;
         group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
         for (int j = j_begin; j < j_end; ++j, ++it) {
           const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          trace_ev(p.trace, 2, ntrace, 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
           bulk_g2s(smem_base + s * stage_bytes + a_bytes, reinterpret_cast<const uint8_t *>(p.Wimg) + (size_t)j * b_bytes, b_bytes,
                    bar_full + 8 * s);
@@ -272,17 +328,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(N);
       uint32_t it = 0, tcount = 0;
+      int ntrace = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         int j_begin, j_end;
         group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
         mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);      // epilogue drained this accumulator stage
         tc_fence_after();
+        trace_ev(p.trace, 3, ntrace, 1);
         const uint32_t tmem_d = tmem_base + as * (uint32_t)N;
         for (int j = j_begin; j < j_end; ++j, ++it) {
           const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
+          trace_ev(p.trace, 3, ntrace, 2);
           const uint32_t a_big = smem_base + s * stage_bytes, a_small = a_big + kABytes;
           const uint32_t b_big = a_big + a_bytes, b_small = b_big + (uint32_t)N * 128u;
           const uint64_t dab = make_desc(a_big), dbb = make_desc(b_big);
@@ -305,11 +365,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     // ===================== epilogue =====================
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     uint32_t tcount = 0;
+    int ntrace = 0;
+    const bool tracer = threadIdx.x == kEpiWarp0 * 32;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
       const int tile = item / p.n_groups;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      if (tracer) trace_ev(p.trace, 4, ntrace, 100 + (int)tcount);
       mbar_wait(bar_acc_full + 8 * as, aph);
       tc_fence_after();
+      if (tracer) trace_ev(p.trace, 4, ntrace, 1);
       const int h = tile * kTileM + q * 32 + lane;
       float *yrow = p.Y + (int64_t)h * p.ldY;
       for (int cb = 0; cb < N; cb += 32) {
@@ -333,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * as);
+      if (tracer) trace_ev(p.trace, 4, ntrace, 2);
     }
   }
 
@@ -392,7 +457,8 @@ extern "C" int efgh_bcl_bias_act(float *Y, int64_t ldY, int M, int64_t h, const 
 
 static int conv_tc_stages(int N, int F, int nsplit, size_t *smem_out) {
   const size_t stage = (size_t)(kABytes + N * 128) * (nsplit == 3 ? 2 : 1);
-  const size_t fixed = (size_t)F * kTileM * 8 + 8 * (2 * kMaxStages + 4) + 16 + 1024;
+  const size_t fixed = 8 * (2 * kMaxStages + 4) + 16 + 1024;
+  (void)F;
   int stages = (int)((220 * 1024 - fixed) / stage);
   if (stages > kMaxStages) stages = kMaxStages;
   if (smem_out) *smem_out = fixed + (size_t)stages * stage;
@@ -401,7 +467,7 @@ static int conv_tc_stages(int N, int F, int nsplit, size_t *smem_out) {
 
 extern "C" int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit) {
   if (!(nsplit == 1 || nsplit == 3)) return 0;
-  if (C <= 0 || C % 4 != 0 || M < 16 || M > 256 || M % 32 != 0 || F < 1 || F > 64) return 0;
+  if (C <= 0 || C % 4 != 0 || M < 16 || M > 256 || M % 32 != 0 || F < 1) return 0;
   return conv_tc_stages(M, F, nsplit, nullptr) >= 2;
 }
 
@@ -429,7 +495,7 @@ extern "C" int efgh_bcl_conv_tc_groups(int K) {
   return (chunks + kGroupChunks - 1) / kGroupChunks;
 }
 
-extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *row_scale, const float *in_bias,
+extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *in_bias,
                                 int in_act, const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h,
                                 const int32_t *h_dev, const float *Wimg, const float *bias, int M, int act, float *Y,
                                 int64_t ldY, int nsplit, int accumulate, void *stream) {
@@ -439,11 +505,12 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   if (h == 0) return EFGH_OK;
   EFGH_REQUIRE(X && Wimg && Y, "efgh_bcl_conv_tc: null pointer");
   EFGH_REQUIRE(ldX % 4 == 0 && ldY % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0,
+                   (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(in_bias) & 15) == 0,
                "efgh_bcl_conv_tc: X, Y and Wimg must be 16-byte aligned with leading dimensions multiple of 4");
   EFGH_REQUIRE(idx_bits == 32 || idx_bits == 64, "efgh_bcl_conv_tc: idx_bits must be 32 or 64");
   ConvParams p;
-  p.X = X; p.ldX = ldX; p.C = C; p.row_scale = row_scale; p.nbr = nbr; p.nbr_ld = nbr_ld; p.F = F;
+  p.trace = g_conv_trace;
+  p.X = X; p.ldX = ldX; p.C = C; p.nbr = nbr; p.nbr_ld = nbr_ld; p.F = F;
   p.h_host = (int)h; p.h_dev = h_dev; p.Wimg = Wimg; p.bias = bias; p.N = M; p.act = act; p.Y = Y; p.ldY = ldY;
   p.in_bias = in_bias; p.in_act = in_act; p.accumulate = accumulate;
   p.n_chunks = (F * C + kChunkK - 1) / kChunkK;

@@ -74,7 +74,6 @@ class ScanPipeline(object):
                     "next": torch.empty((3, h_cap), dtype=f32, device=dev) if li != self.nlev - 1 else None,
                     "S": torch.empty((h_cap + 1, cin), dtype=f32, device=dev),
                     "wsum": torch.empty((h_cap + 1,), dtype=f32, device=dev),
-                    "inv": torch.empty((h_cap + 1,), dtype=f32, device=dev),
                     "Y": torch.empty((h_cap, cmid), dtype=f32, device=dev),
                     "Z": torch.empty((h_cap, cout), dtype=f32, device=dev),
                 }
@@ -150,10 +149,9 @@ class ScanPipeline(object):
                 ck(L.efgh_bcl_scatter(prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev, lv["bary"].data_ptr(), n_cap,
                                       lv["loff32"].data_ptr(), 32, n_cap, 1, S + 16, cin, None, s), "efgh_bcl_scatter")
                 if self.use_norm:
-                    ck(L.efgh_bcl_inv_norm(lv["wsum"].data_ptr(), lv["inv"].data_ptr(), h_cap + 1, h_dev, 1, s),
-                       "efgh_bcl_inv_norm")
+                    ck(L.efgh_bcl_normalize(S, cin, cin, lv["wsum"].data_ptr(), None, h_cap + 1, h_dev, 1, s),
+                       "efgh_bcl_normalize")
             timed("L%d.splat" % li, splat)
-            inv_ptr = lv["inv"].data_ptr() if self.use_norm else None
             if lv["tc"]:
                 # conv1 on tensor cores: long contraction -> partial sums added in L2, bias + ReLU deferred to
                 # conv2's loader (in_bias / in_act), so Y holds raw sums and is never re-written
@@ -162,17 +160,17 @@ class ScanPipeline(object):
                 def conv1():
                     if split:
                         ck(L.efgh_bcl_zero(lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, h_cap, h_dev, 0, s), "efgh_bcl_zero")
-                    ck(L.efgh_bcl_conv_tc(S, cin, cin, inv_ptr, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"], h_cap, h_dev,
+                    ck(L.efgh_bcl_conv_tc(S, cin, cin, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"], h_cap, h_dev,
                                           lv["img0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
                                           lv["cmid"], self.nsplit, 1 if split else 0, s), "efgh_bcl_conv_tc")
                 timed("L%d.conv1" % li, conv1)
                 timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv_tc(
-                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, lv["b0"].data_ptr() if split else None, _ACT["relu"], None, 32, 0,
+                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], lv["b0"].data_ptr() if split else None, _ACT["relu"], None, 32, 0,
                     1, h_cap, h_dev, lv["img1"].data_ptr(), lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(),
                     lv["cout"], self.nsplit, 0, s), "efgh_bcl_conv_tc"))
             else:
                 timed("L%d.conv1" % li, lambda: ck(L.efgh_bcl_conv(
-                    S, cin, cin, inv_ptr, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"],
+                    S, cin, cin, None, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"],
                     h_cap, h_dev, lv["Wt0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
                     lv["cmid"], 0, s), "efgh_bcl_conv"))
                 timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv(

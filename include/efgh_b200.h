@@ -129,6 +129,11 @@ int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int 
 int efgh_bcl_inv_norm(const float *wsum, float *inv, int64_t rows, const int32_t *rows_dev, int rows_extra,
                       void *stream);
 
+/* Density normalisation in place (bilateralNN.py:210-211): S[r, :] *= 1 / (wsum[r] + 1e-5); the factor is also
+ * written to inv_out[r] when inv_out != NULL (the backward pass needs it). */
+int efgh_bcl_normalize(float *S, int64_t ldS, int C, const float *wsum, float *inv_out, int64_t rows,
+                       const int32_t *rows_dev, int rows_extra, void *stream);
+
 /* Slice (bilateralNN.py:251-261) and the adjoint of splat:
  *   out[c,n] = sum_r w[r,n] * Z[off[r,n]+row_shift, c] * (row_scale ? row_scale[row] : 1) + (bias ? bias[c] : 0) */
 int efgh_bcl_gather(const float *Z, int64_t ldZ, int C, const float *row_scale, int64_t n, const int32_t *n_dev,
@@ -153,7 +158,9 @@ int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *row_scale, co
  * takes into the swizzled shared-memory image the kernel streams in with bulk copies (pack once per weight
  * update; efgh_bcl_packed_weight_bytes gives the buffer size, 16-byte aligned).
  * efgh_bcl_conv_tc_supported: 1 if the shape can run here (C % 4 == 0, M in {32,64,...,256}), else use
- * efgh_bcl_conv.  X, Y 16-byte aligned, ldX and ldY multiples of 4.
+ * efgh_bcl_conv.  X, Y 16-byte aligned, ldX and ldY multiples of 4.  Unlike efgh_bcl_conv there is no
+ * row_scale argument: normalise the splat matrix first (efgh_bcl_normalize) - rows are copied from L2 into
+ * the tensor core's shared-memory tiles asynchronously, without passing through registers.
  *
  * Long contractions are cut into efgh_bcl_conv_tc_groups(K) partial sums (tensor-core accumulation rounds
  * toward zero, so chains are kept short; the cut is also the split-K that fills the GPU on small lattices).
@@ -167,7 +174,7 @@ int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit);
 int efgh_bcl_conv_tc_groups(int K);
 size_t efgh_bcl_packed_weight_bytes(int K, int M, int nsplit);
 int efgh_bcl_pack_weights(const float *Wt, int K, int M, int nsplit, float *Wimg, void *stream);
-int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *row_scale, const float *in_bias, int in_act,
+int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *in_bias, int in_act,
                      const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev,
                      const float *Wimg, const float *bias, int M, int act, float *Y, int64_t ldY, int nsplit,
                      int accumulate, void *stream);

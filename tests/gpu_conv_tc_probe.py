@@ -16,10 +16,11 @@ for (H, C, F, M) in [(300, 36, 15, 32), (1000, 36, 15, 64), (5000, 68, 15, 128),
     Xin = X if F > 1 else X[1:].contiguous()
     sc = scale if F > 1 else None
     B.CONV_PRECISION = "fp32"
-    ref = B.conv(Xin, sc, nbr, Wt, bias, 1, H)
+    Xn = (Xin * sc[:, None]).contiguous() if sc is not None else Xin
+    ref = B.conv(Xn, nbr, Wt, bias, 1, H)
     for prec in ("3xtf32", "tf32"):
         B.CONV_PRECISION = prec
-        got = B.conv(Xin, sc, nbr, Wt, bias, 1, H)
+        got = B.conv(Xn, nbr, Wt, bias, 1, H)
         torch.cuda.synchronize()
         err = float((got - ref).abs().max() / ref.abs().max())
         print("H=%d C=%d F=%d M=%d %s rel err %.3e" % (H, C, F, M, prec, err), flush=True)
@@ -31,7 +32,8 @@ nbr = torch.randint(-1, H, (1, F, H), device=dev, dtype=torch.int32)
 Wt0 = torch.randn(F * C, M1, device=dev) * 0.05; b0 = torch.randn(M1, device=dev)
 Wt1 = torch.randn(M1, M2, device=dev) * 0.1; b1 = torch.randn(M2, device=dev)
 B.CONV_PRECISION = "fp32"
-ref = B.conv(B.conv(X, scale, nbr, Wt0, b0, 1, H), None, None, Wt1, b1, 0, H)
+X = (X * scale[:, None]).contiguous()
+ref = B.conv(B.conv(X, nbr, Wt0, b0, 1, H), None, Wt1, b1, 0, H)
 for ns in (3, 1):
     img0 = torch.empty(L.efgh_bcl_packed_weight_bytes(F * C, M1, ns) // 4, device=dev)
     img1 = torch.empty(L.efgh_bcl_packed_weight_bytes(M1, M2, ns) // 4, device=dev)
@@ -39,9 +41,9 @@ for ns in (3, 1):
     _capi.check(L.efgh_bcl_pack_weights(Wt0.data_ptr(), F * C, M1, ns, img0.data_ptr(), st), "pack")
     _capi.check(L.efgh_bcl_pack_weights(Wt1.data_ptr(), M1, M2, ns, img1.data_ptr(), st), "pack")
     Y = torch.zeros(H, M1, device=dev); Z = torch.empty(H, M2, device=dev)
-    _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), C, C, scale.data_ptr(), None, 0, nbr.data_ptr(), 32, H, F, H, None, img0.data_ptr(),
+    _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), C, C, None, 0, nbr.data_ptr(), 32, H, F, H, None, img0.data_ptr(),
                                    None, M1, 0, Y.data_ptr(), M1, ns, 1, st), "conv1")
-    _capi.check(L.efgh_bcl_conv_tc(Y.data_ptr(), M1, M1, None, b0.data_ptr(), 1, None, 32, 0, 1, H, None, img1.data_ptr(),
+    _capi.check(L.efgh_bcl_conv_tc(Y.data_ptr(), M1, M1, b0.data_ptr(), 1, None, 32, 0, 1, H, None, img1.data_ptr(),
                                    b1.data_ptr(), M2, 0, Z.data_ptr(), M2, ns, 0, st), "conv2")
     torch.cuda.synchronize()
     print("chain nsplit=%d groups=%d rel err %.3e" % (ns, L.efgh_bcl_conv_tc_groups(F * C), float((Z - ref).abs().max() / ref.abs().max())), flush=True)

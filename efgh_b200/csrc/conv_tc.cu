@@ -1,42 +1,59 @@
 // Lattice convolution on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 //
-//   Y[h, m] = act(bias[m] + sum_{f,c} X[nbr[f,h]+1, c] * scale[row] * W[(f,c), m])
+//   Y[h, m] (+)= act(bias[m] + sum_{f,c} X[nbr[f,h]+1, c] * W[(f,c), m])
 //
-// reference nets/bilateralNN.py:240-244: advanced-index gather that materialises (1, C, F, H), then a cuDNN
-// (F,1) convolution.  Here the gather IS the A-operand loader of a warp-specialised GEMM:
+// reference nets/bilateralNN.py:240-244 gathers a (1, C, F, H) tensor (218 MB at level 0) and runs a cuDNN
+// (F,1) convolution over it.  Here the gather is the A-operand path of a warp-specialised GEMM and the
+// gathered tensor only ever exists 128 rows x 32 floats at a time:
 //
-//   warps 0-7   gather producers, two teams of 128 (thread = tile row): cp.async 16-byte pieces of neighbour
-//               rows of the (already normalised) vertex-major splat matrix from L2 straight into the
-//               128-byte-swizzled K-major A tile (the UMMA canonical layout), several chunks in flight; then
-//               split each landed value in place into a TF32-exact "big" part and the fp32 remainder "small"
-//   warp  8     MMA issuer: one thread issues tcgen05.mma kind::tf32, M=128 x N x K=8, accumulators in TMEM.
-//               3xTF32: D += A_small*B_big + A_big*B_small + A_big*B_big  (fp32-equivalent accuracy; the
-//               dropped small*small term is 2^-22 relative), or a single TF32 pass when nsplit == 1
-//   warp  9     weight loader: one thread issues cp.async.bulk (TMA engine, UBLKCP) per K chunk; the weights
-//               were packed once (k_pack_weights) into the exact swizzled shared-memory image, big | small
-//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers, bias + activation, row-contiguous 16-byte stores
+//   warps 0-15  gather producers, four teams of 128 threads (thread = one vertex row of the 128-row tile);
+//               team t handles K chunks t, t+4, ... of every work item, so four chunks are always being
+//               prepared concurrently (one warp per scheduler per team; a single warp is latency-bound).
+//               Per K chunk (32 floats = 128 B of the row) a team
+//                 1. cp.async's (LDGSTS, zero-fill for absent neighbours) whole 128-byte pieces of neighbour
+//                    rows of the normalised, vertex-major splat matrix from L2 into a warp-PRIVATE slot of a
+//                    shared-memory ring (8 lanes per row piece = one cache line per 8 lanes) - several chunks
+//                    in flight, no barrier needed because only the issuing warp reads its slot back;
+//                 2. each thread re-reads its row's landed 128 B, applies the optional deferred bias + ReLU of a split-K
+//                    producer, splits each value into a TF32-exact "big" part and the fp32 remainder
+//                    "small", and writes both straight into TENSOR MEMORY with tcgen05.st (lane = row,
+//                    32 columns each) - the A operand never goes back through shared memory;
+//   warp  16    MMA issuer: one thread issues tcgen05.mma kind::tf32 with A from TMEM and B from shared
+//               memory, M=128 x N x K=8, fp32 accumulators in TMEM.  3xTF32:
+//               D += A_small*B_big + A_big*B_small + A_big*B_big (the dropped small*small term is 2^-22
+//               relative), or one TF32 pass when nsplit == 1;
+//   warp  17    weight loader: one thread issues cp.async.bulk (TMA engine, UBLKCP) per K chunk; the
+//               weights were packed once (k_pack_weights) into the swizzled K-major image, big | small;
+//   warps 18-21 epilogue: tcgen05.ld accumulators -> registers, then either bias + activation + 16-byte
+//               row stores, or red.add.v4 of the raw partial sum into Y (split-K / chain cut, see below).
 //
-// Two TMEM accumulator stages (2 x N <= 512 columns) let the epilogue of tile t overlap the mainloop of
-// tile t+1; a ring of shared-memory stages (full/empty mbarriers) decouples gather, weight load and MMA.
-// Persistent CTAs, one per SM, stride over 128-vertex tiles; the vertex count is read from device memory.
+// Tensor-core accumulation rounds toward zero, so the error of a long accumulation chain grows linearly
+// with its length; chains are cut every kGroupChunks chunks and the partial sums are added in L2 with
+// round-to-nearest atomics.  The same cut is the split-K that keeps all 148 SMs busy on the small
+// lattices of the deep levels.  Work item = (128-vertex tile, K group); persistent CTAs, one per SM,
+// stride over the items; the vertex count is read from device memory.
+//
+// TMEM map (512 columns): [accumulators: acc_stages x N] [A operand: 4 teams x (32 big | 32 small)].
 #include "common.cuh"
 
 static unsigned long long *g_conv_trace = nullptr;
 // Debug hook (not part of the public header): device buffer of 5 roles x 512 x 2 u64 that CTA 0 fills with
 // (event, globaltimer) pairs, or NULL to disable.
 extern "C" void efgh_debug_set_conv_trace(unsigned long long *buf) { g_conv_trace = buf; }
+static int g_conv_flags = 0;   // debug: bit0 = skip the gather copies (wrong results, timing only); bits 4-7 = raw-slot override
+extern "C" void efgh_debug_set_conv_flags(int flags) { g_conv_flags = flags; }
 
 namespace efgh {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 32;                  // floats per K chunk = one 128-byte swizzle row
-constexpr int kProducerWarps = 8;
-constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kMmaWarp = 8, kTmaWarp = 9, kEpiWarp0 = 10;
-constexpr int kThreads = (kEpiWarp0 + 4) * 32;  // 448
-constexpr int kMaxStages = 6;
-constexpr int kABytes = kTileM * 128;        // one A tile (128 rows x 128 B)
+constexpr int kChunkK = 32;                  // floats per K chunk = one 128-byte row piece
+constexpr int kTeams = 4;                    // producer teams; team t converts chunks t, t+4, ... of every item
+constexpr int kProducerWarps = 4 * kTeams;
+constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1, kEpiWarp0 = kProducerWarps + 2;
+constexpr int kThreads = (kEpiWarp0 + 4) * 32;  // 704
+constexpr int kMaxRaw = 3;                   // raw-row slots per producer warp
+constexpr int kRawSlotBytes = kTeams * kTileM * 128;  // one raw slot for all teams (512 threads x 128 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,8 +78,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// Same, but yields issue slots between polls: used by roles whose wake-up latency is not critical (their
+// spin loops would otherwise compete with the producer warps on the same scheduler).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -72,17 +106,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                : "memory");
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[tmem] * B[smem descriptor].  Executed by the WHOLE (converged) MMA warp; one elected lane
+// issues.  Keeping the warp converged lets the compiler hold the operands in uniform registers - under an
+// `if (lane == 0)` it wraps every tcgen05.mma in a value-uniformising loop.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
 }
 
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO = 64 x 16 B), descriptor version 1 (sm_100)
@@ -112,6 +156,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   if (act == 2) return v > 0.f ? v : 0.1f * v;
@@ -131,14 +196,16 @@ __device__ __forceinline__ void trace_ev(unsigned long long *trace, int role, in
 }
 
 struct ConvParams {
-  unsigned long long *trace;
+  unsigned long long *trace; int dbg_flags;
   const float *X; int64_t ldX; int C;
   const float *in_bias; int in_act;     // optional input transform x = act(x + in_bias[c]) (deferred epilogue of a split-K producer)
   const void *nbr; int64_t nbr_ld; int F;
   int h_host; const int32_t *h_dev;
   const float *Wimg; const float *bias; int N; int act;
   float *Y; int64_t ldY;
-  int n_chunks; int n_groups; int stages; int tmem_cols;
+  int n_chunks; int n_groups;
+  int b_stages, raw_slots, acc_stages;
+  uint32_t magic_c;                     // ceil(2^32 / C): k / C == __umulhi(k, magic_c) for the k range used here
   int accumulate;                       // 1: red.add raw partial sums into pre-zeroed Y (bias/act deferred); 0: store act(bias + acc)
 };
 
@@ -149,40 +216,59 @@ __device__ __forceinline__ void group_range(int n_chunks, int n_groups, int g, i
   end = begin + base + (g < rem ? 1 : 0);
 }
 
+// Position in one producer team's chunk sequence: every item of this CTA, chunks j_begin+team, +kTeams, ...
+struct TeamPos {
+  int item, j, j_end, tile;
+  __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
+  __device__ __forceinline__ void settle(const ConvParams &p, int n_items, int team) {   // skip items with no chunk for this team
+    while (item < n_items) {
+      int jb, je;
+      group_range(p.n_chunks, p.n_groups, item % p.n_groups, jb, je);
+      if (jb + team < je) { j = jb + team; j_end = je; tile = item / p.n_groups; return; }
+      item += (int)gridDim.x;
+    }
+  }
+  __device__ __forceinline__ void init(const ConvParams &p, int n_items, int team) {
+    item = (int)blockIdx.x; j = j_end = tile = 0;
+    settle(p, n_items, team);
+  }
+  __device__ __forceinline__ void advance(const ConvParams &p, int n_items, int team) {
+    j += kTeams;
+    if (j >= j_end) { item += (int)gridDim.x; settle(p, n_items, team); }
+  }
+};
+
 template <typename IdxT, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A_big | A_small? | B_big | B_small?)] [barriers]
+  // carve: [B ring: b_stages x (B_big | B_small?)] [raw ring: raw_slots x 256 threads x 128 B] [barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int N = p.N;
-  const uint32_t a_bytes = kABytes * (NSPLIT == 3 ? 2 : 1);
   const uint32_t b_bytes = (uint32_t)N * 128u * (NSPLIT == 3 ? 2 : 1);
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages,
-                 bar_acc_full = bar_empty + 8 * kMaxStages, bar_acc_empty = bar_acc_full + 16;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 4);
+  const uint32_t raw_base = smem_base + (uint32_t)p.b_stages * b_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes);
+  // barrier map (8 B each): A_full[4 teams] A_empty[4] (2 spare each) B_full[4] B_empty[4] acc_full[2] acc_empty[2]
+  const uint32_t bar_a_full = smem_u32(bars), bar_a_empty = bar_a_full + 8 * 6, bar_b_full = bar_a_empty + 8 * 6,
+                 bar_b_empty = bar_b_full + 8 * 4, bar_acc_full = bar_b_empty + 8 * 4, bar_acc_empty = bar_acc_full + 16;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
   const int n_tiles = (H + kTileM - 1) / kTileM;
   const int n_items = n_tiles * p.n_groups;
   const int K = p.F * p.C;
+  constexpr uint32_t kAStageCols = NSPLIT == 3 ? 64 : 32;
+  const uint32_t a_ring_col = (uint32_t)(p.acc_stages * N);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, 128);
-    }
+    for (int i = 0; i < 6; ++i) { mbar_init(bar_a_full + 8 * i, 128); mbar_init(bar_a_empty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, 128); }
     fence_barrier_init();
   }
   if (warp == kTmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -192,173 +278,199 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
 
   if (warp < kProducerWarps) {
     // ===================== gather producers =====================
-    // Two teams of 128 threads (thread = tile row) alternate over this CTA's work items, so one team's
-    // pipeline drain / neighbour-table load overlaps the other team's copies.  Per K chunk a thread
-    //   1. cp.async's (LDGSTS, zero-fill for absent neighbours) the 8 x 16-byte pieces of its row straight
-    //      from the vertex-major matrix into the swizzled A tile - up to `depth` chunks in flight, no
-    //      registers held across the L2 latency,
-    //   2. once its own copies have landed, re-reads them, applies the optional deferred bias + activation,
-    //      splits every value into the TF32-exact "big" part (written back in place) and the fp32 remainder
-    //      "small" (second tile), fences the generic->async proxy and arrives on the stage's full barrier.
     const int team = warp >> 2;
-    const int r = threadIdx.x & (kTileM - 1);
-    const uint32_t swz = (uint32_t)(r & 7);
-    const int depth = min(4, p.stages - 1);
-    uint32_t it = 0;       // global chunk sequence number of this CTA (both teams track all items)
-    int k_item = 0, ntrace = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k_item) {
-      const int tile = item / p.n_groups, grp = item - tile * p.n_groups;
-      int j_begin, j_end;
-      group_range(p.n_chunks, p.n_groups, grp, j_begin, j_end);
-      if ((k_item & 1) != team) { it += (uint32_t)(j_end - j_begin); continue; }
-      const int h = tile * kTileM + r;
-      const bool has_next = item + (int)gridDim.x < n_items;
-      // Neighbour rows of this thread's vertex for filter taps f, f+1, f+2 live in registers and are refilled
-      // two taps ahead of use (coalesced 512-byte reads across the team), so no index table / barrier is needed.
-      int f_cur = (j_begin * kChunkK) / p.C;
-      int c_cur = j_begin * kChunkK - f_cur * p.C;
-      auto fetch_row = [&](int f) -> int {
-        if (h >= H || f >= p.F) return -1;
-        if (!p.nbr) return h;
-        const int row = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h) + 1;
-        return row == 0 ? -1 : row;                                          // sink row: all zeros
-      };
-      int row0 = fetch_row(f_cur), row1 = fetch_row(f_cur + 1), row2 = fetch_row(f_cur + 2);
-      // Stage slots are claimed in global chunk order: this team may start claiming only after the other team
-      // has claimed every slot of the previous item (mbarrier parity cannot tell phases two apart).
-      if (k_item > 0) asm volatile("bar.sync %0, 256;" ::"r"(3 + (team ^ 1)) : "memory");
-      bool handed_off = false;
+    const int r = (warp & 3) * 32 + lane;                                     // tile row owned by this thread
+    const uint32_t swz = (uint32_t)(lane & 7);
+    const uint32_t warp_raw = raw_base + (uint32_t)warp * 4096u;              // this warp's 32 rows x 128 B (+ slot * kRawSlotBytes)
+    const uint32_t my_raw = warp_raw + (uint32_t)lane * 128u;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;             // TMEM lanes this warp may touch
+    const uint32_t a_t = tmem_base + lane_base + a_ring_col + (uint32_t)team * kAStageCols;
+    const bool tracer = r == 0 && team < 2;
+    int ntrace = 0;
 
-      auto issue = [&](int j, uint32_t seq) {
-        const uint32_t s = seq % p.stages, ph = (seq / p.stages) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t a_big = smem_base + s * stage_bytes + (uint32_t)r * 128u;
-        int k = j * kChunkK;
+    // neighbour rows (taps f, f+1) of this thread's vertex for the chunk at `pos`; -1 = absent -> zeros
+    auto fetch_rows = [&](const TeamPos &pos, int &ra, int &rb) {
+      ra = rb = -1;
+      if (!pos.valid(n_items)) return;
+      const int h = pos.tile * kTileM + r;
+      if (h >= H) return;
+      if (!p.nbr) { ra = h; return; }
+      const int f = (int)__umulhi((uint32_t)(pos.j * kChunkK), p.magic_c);
+      const int a = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h) + 1;
+      ra = a == 0 ? -1 : a;                                                   // sink row: all zeros
+      if (f + 1 < p.F) {
+        const int b = load_idx<IdxT>(p.nbr, (f + 1) * p.nbr_ld + h) + 1;
+        rb = b == 0 ? -1 : b;
+      }
+    };
+
+    TeamPos pi, pc, pp;                                     // issue / convert / row-prefetch positions
+    pi.init(p, n_items, team);
+    pc = pi; pp = pi;
+    int r0a, r0b, r1a, r1b, r2a, r2b;                       // row pairs for pi, pi+1, pi+2
+    fetch_rows(pp, r0a, r0b);
+    pp.advance(p, n_items, team); fetch_rows(pp, r1a, r1b);
+    pp.advance(p, n_items, team); fetch_rows(pp, r2a, r2b);
+    uint32_t n_inflight = 0, slot_i = 0, slot_c = 0, a_ph = 0;
+    bool st_pending = false;
+
+    while (pc.valid(n_items)) {
+      while (pi.valid(n_items) && (int)n_inflight < p.raw_slots) {
+        // 8 lanes cooperate on one row (8 x 16 B = one full 128-byte line), 4 rows per instruction, so every
+        // LDGSTS touches whole cache lines; the neighbour row index comes from the lane that owns the row.
+        const uint32_t dst = warp_raw + slot_i * kRawSlotBytes;
+        const int k0 = pi.j * kChunkK;
+        const int f = (int)__umulhi((uint32_t)k0, p.magic_c);
+        const int cu = k0 - f * p.C + 4 * (lane & 7);
+        const bool wrap = cu >= p.C;
+        const int c_u = wrap ? cu - p.C : cu;
+        const bool in_k = k0 + 4 * (lane & 7) < K;
+        int rows[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int row = k < K ? row0 : -1;
-          const float *src = row >= 0 ? p.X + (int64_t)row * p.ldX + c_cur : p.X;
-          const uint32_t nbytes = row >= 0 ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_big + (((uint32_t)u ^ swz) << 4)), "l"(src), "r"(nbytes)
+        for (int i = 0; i < 8; ++i) {                         // all shuffles first: they pipeline
+          const int R = 4 * i + (lane >> 3);
+          const int ra = __shfl_sync(0xffffffffu, r0a, R), rb = __shfl_sync(0xffffffffu, r0b, R);
+          rows[i] = in_k ? (wrap ? rb : ra) : -1;
+        }
+        const uint32_t dst_lane = dst + ((uint32_t)lane >> 3) * 128u;
+        const uint32_t u_lane = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t R7 = ((uint32_t)(4 * i) + ((uint32_t)lane >> 3)) & 7u;
+          const float *src = rows[i] >= 0 ? p.X + (int64_t)rows[i] * p.ldX + c_u : p.X;
+          const uint32_t nbytes = rows[i] >= 0 ? 16u : 0u;
+          if (!(p.dbg_flags & 1))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_lane + (uint32_t)i * 512u + ((u_lane ^ R7) << 4)), "l"(src),
+                       "r"(nbytes)
                        : "memory");
-          k += 4; c_cur += 4;
-          if (c_cur >= p.C) {
-            c_cur = 0; ++f_cur;
-            row0 = row1; row1 = row2; row2 = fetch_row(f_cur + 2);
-          }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      auto convert = [&](int j, uint32_t seq) {
-        const uint32_t s = seq % p.stages;
-        const uint32_t a_big = smem_base + s * stage_bytes + (uint32_t)r * 128u, a_small = a_big + kABytes;
-        int c = (j * kChunkK) % p.C;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t off = ((uint32_t)u ^ swz) << 4;
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a_big + off) : "memory");
-          if (p.in_bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.in_bias + c));
-            v.x = act_apply(v.x + b.x, p.in_act); v.y = act_apply(v.y + b.y, p.in_act);
-            v.z = act_apply(v.z + b.z, p.in_act); v.w = act_apply(v.w + b.w, p.in_act);
-          }
-          float4 big;
-          big.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          big.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          big.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          big.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_big + off), "f"(big.x), "f"(big.y), "f"(big.z), "f"(big.w) : "memory");
-          if (NSPLIT == 3) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_small + off), "f"(v.x - big.x), "f"(v.y - big.y),
-                         "f"(v.z - big.z), "f"(v.w - big.w)
-                         : "memory");
-          }
-          c += 4;
-          if (c >= p.C) c = 0;
-        }
-        fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(bar_full + 8 * s);
-      };
-
-      int ji = j_begin, jc = j_begin;
-      const bool tracer = (threadIdx.x & 127) == 0;
-      if (tracer) trace_ev(p.trace, team, ntrace, 100 + k_item);
-      while (jc < j_end) {
-        while (ji < j_end && ji - jc < depth) {
-          issue(ji, it + (uint32_t)(ji - j_begin)); ++ji;
-          if (tracer) trace_ev(p.trace, team, ntrace, 1);
-        }
-        if (ji == j_end && !handed_off) {
-          handed_off = true;
-          if (has_next) asm volatile("bar.arrive %0, 256;" ::"r"(3 + team) : "memory");
-        }
-        const int pending = ji - jc - 1;         // younger groups that may still be in flight
-        if (pending >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
-        else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (tracer) trace_ev(p.trace, team, ntrace, 2);
-        convert(jc, it + (uint32_t)(jc - j_begin));
-        if (tracer) trace_ev(p.trace, team, ntrace, 3);
-        ++jc;
+        pi.advance(p, n_items, team);
+        r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
+        pp.advance(p, n_items, team); fetch_rows(pp, r2a, r2b);
+        ++n_inflight;
+        if (++slot_i == (uint32_t)p.raw_slots) slot_i = 0;
+        if (tracer) trace_ev(p.trace, team, ntrace, 1);
       }
-      it += (uint32_t)(j_end - j_begin);
+      if (st_pending) {                                     // previous chunk's TMEM stores had a whole issue to complete
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(bar_a_full + 8 * team);
+        st_pending = false;
+      }
+      if (n_inflight >= 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else if (n_inflight == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();                                         // the row pieces were fetched by 8 different lanes of this warp
+      if (tracer) trace_ev(p.trace, team, ntrace, 2);
+
+      // ---- landed chunk -> registers -> (bias/act) -> big | small -> tensor memory, 16 columns at a time
+      const uint32_t src = my_raw + slot_c * kRawSlotBytes;
+      const int cb0 = p.in_bias ? (pc.j * kChunkK - (int)__umulhi((uint32_t)(pc.j * kChunkK), p.magic_c) * p.C) : 0;
+      bool waited = false;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[4 * u]), "=f"(v[4 * u + 1]), "=f"(v[4 * u + 2]), "=f"(v[4 * u + 3])
+                       : "r"(src + ((((uint32_t)(4 * hlf + u)) ^ swz) << 4)));
+        }
+        if (p.in_bias) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int c = cb0 + 16 * hlf + 4 * u;
+            if (c >= p.C) c -= p.C;
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.in_bias + c));
+            v[4 * u] = act_apply(v[4 * u] + b.x, p.in_act);
+            v[4 * u + 1] = act_apply(v[4 * u + 1] + b.y, p.in_act);
+            v[4 * u + 2] = act_apply(v[4 * u + 2] + b.z, p.in_act);
+            v[4 * u + 3] = act_apply(v[4 * u + 3] + b.w, p.in_act);
+          }
+        }
+        uint32_t big[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) big[i] = __float_as_uint(v[i]) & 0xffffe000u;
+        if (!waited) {                                      // MMA done with this team's previous chunk
+          mbar_wait(bar_a_empty + 8 * team, a_ph ^ 1);
+          tc_fence_after();
+          waited = true;
+        }
+        tmem_st16(a_t + 16 * hlf, big);
+        if (NSPLIT == 3) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) big[i] = __float_as_uint(v[i] - __uint_as_float(big[i]));
+          tmem_st16(a_t + 32 + 16 * hlf, big);
+        }
+      }
+      st_pending = true;
+      a_ph ^= 1;
+      if (tracer) trace_ev(p.trace, team, ntrace, 3);
+      pc.advance(p, n_items, team);
+      --n_inflight;
+      if (++slot_c == (uint32_t)p.raw_slots) slot_c = 0;
+    }
+    if (st_pending) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar_a_full + 8 * team);
     }
   } else if (warp == kTmaWarp) {
     // ===================== weight loader (TMA bulk copies) =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      int ntrace = 0;
+      uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int j_begin, j_end;
         group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
-        for (int j = j_begin; j < j_end; ++j, ++it) {
-          const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          trace_ev(p.trace, 2, ntrace, 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-          bulk_g2s(smem_base + s * stage_bytes + a_bytes, reinterpret_cast<const uint8_t *>(p.Wimg) + (size_t)j * b_bytes, b_bytes,
-                   bar_full + 8 * s);
+        for (int j = j_begin; j < j_end; ++j) {
+          mbar_wait_relaxed(bar_b_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_b_full + 8 * s, b_bytes);
+          bulk_g2s(smem_base + s * b_bytes, reinterpret_cast<const uint8_t *>(p.Wimg) + (size_t)j * b_bytes, b_bytes, bar_b_full + 8 * s);
+          if (++s == (uint32_t)p.b_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
       const uint32_t idesc = make_idesc(N);
-      uint32_t it = 0, tcount = 0;
+      uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0;
       int ntrace = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         int j_begin, j_end;
         group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
-        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
+        const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
+        const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+        if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
         mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);      // epilogue drained this accumulator stage
         tc_fence_after();
-        trace_ev(p.trace, 3, ntrace, 1);
         const uint32_t tmem_d = tmem_base + as * (uint32_t)N;
-        for (int j = j_begin; j < j_end; ++j, ++it) {
-          const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-          mbar_wait(bar_full + 8 * s, ph);
+        for (int j = j_begin; j < j_end; ++j) {
+          const uint32_t team = (uint32_t)(j - j_begin) & (kTeams - 1);
+          mbar_wait(bar_a_full + 8 * team, (pha_bits >> team) & 1);
+          mbar_wait(bar_b_full + 8 * sb, phb);
           tc_fence_after();
-          trace_ev(p.trace, 3, ntrace, 2);
-          const uint32_t a_big = smem_base + s * stage_bytes, a_small = a_big + kABytes;
-          const uint32_t b_big = a_big + a_bytes, b_small = b_big + (uint32_t)N * 128u;
-          const uint64_t dab = make_desc(a_big), dbb = make_desc(b_big);
+          if (lane == 0) trace_ev(p.trace, 3, ntrace, 2);
+          const uint32_t a_big = tmem_base + a_ring_col + team * kAStageCols, a_small = a_big + 32;
+          const uint32_t b_big = smem_base + sb * b_bytes, b_small = b_big + (uint32_t)N * 128u;
+          const uint64_t dbb = make_desc(b_big);
           uint32_t acc = j > j_begin;
           if (NSPLIT == 3) {
-            const uint64_t das = make_desc(a_small), dbs = make_desc(b_small);
+            const uint64_t dbs = make_desc(b_small);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) { umma_tf32(tmem_d, das + 2 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
+            for (int k4 = 0; k4 < 4; ++k4) { umma_tf32_ts(tmem_d, a_small + 8 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) umma_tf32(tmem_d, dab + 2 * k4, dbs + 2 * k4, idesc, 1);
+            for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(tmem_d, a_big + 8 * k4, dbs + 2 * k4, idesc, 1);
           }
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) { umma_tf32(tmem_d, dab + 2 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
-          umma_commit(bar_empty + 8 * s);              // frees the smem stage when these MMAs retire
+          for (int k4 = 0; k4 < 4; ++k4) { umma_tf32_ts(tmem_d, a_big + 8 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
+          umma_commit(bar_a_empty + 8 * team);               // frees the team's TMEM A stage when these MMAs retire
+          umma_commit(bar_b_empty + 8 * sb);                 // ... and the weight stage
+          pha_bits ^= 1u << team;
+          if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1; }
         }
-        umma_commit(bar_acc_full + 8 * as);            // accumulator complete -> epilogue
+        umma_commit(bar_acc_full + 8 * as);                  // accumulator complete -> epilogue
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -369,9 +481,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     const bool tracer = threadIdx.x == kEpiWarp0 * 32;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
       const int tile = item / p.n_groups;
-      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
+      const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
       if (tracer) trace_ev(p.trace, 4, ntrace, 100 + (int)tcount);
-      mbar_wait(bar_acc_full + 8 * as, aph);
+      mbar_wait_relaxed(bar_acc_full + 8 * as, aph);
       tc_fence_after();
       if (tracer) trace_ev(p.trace, 4, ntrace, 1);
       const int h = tile * kTileM + q * 32 + lane;
@@ -404,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == kTmaWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -455,20 +568,27 @@ extern "C" int efgh_bcl_bias_act(float *Y, int64_t ldY, int M, int64_t h, const 
   return EFGH_OK;
 }
 
-static int conv_tc_stages(int N, int F, int nsplit, size_t *smem_out) {
-  const size_t stage = (size_t)(kABytes + N * 128) * (nsplit == 3 ? 2 : 1);
-  const size_t fixed = 8 * (2 * kMaxStages + 4) + 16 + 1024;
-  (void)F;
-  int stages = (int)((220 * 1024 - fixed) / stage);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (smem_out) *smem_out = fixed + (size_t)stages * stage;
-  return stages;
+// Resource plan for output width N: TMEM = acc_stages*N + 4 teams x (32|64) A columns <= 512;
+// shared memory = b_stages weight tiles + raw_slots x 64 KB of warp-private row slots.
+static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
+  const int a_cols = nsplit == 3 ? 64 : 32;
+  const int acc_stages = 2 * N + kTeams * a_cols <= 512 ? 2 : 1;
+  if (acc_stages * N + kTeams * a_cols > 512) return false;
+  const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
+  const size_t budget = 220 * 1024 - 1024 - 256;
+  int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
+  if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
+  int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
+  if (raw > kMaxRaw) raw = kMaxRaw;
+  if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; }
+  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + 256 + 1024;
+  return true;
 }
 
 extern "C" int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit) {
   if (!(nsplit == 1 || nsplit == 3)) return 0;
-  if (C <= 0 || C % 4 != 0 || M < 16 || M > 256 || M % 32 != 0 || F < 1) return 0;
-  return conv_tc_stages(M, F, nsplit, nullptr) >= 2;
+  if (C < 32 || C % 4 != 0 || M < 32 || M > 256 || M % 32 != 0 || F < 1) return 0;
+  return conv_tc_plan(M, nsplit, nullptr, nullptr) ? 1 : 0;
 }
 
 extern "C" size_t efgh_bcl_packed_weight_bytes(int K, int M, int nsplit) {
@@ -495,10 +615,10 @@ extern "C" int efgh_bcl_conv_tc_groups(int K) {
   return (chunks + kGroupChunks - 1) / kGroupChunks;
 }
 
-extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *in_bias,
-                                int in_act, const void *nbr, int idx_bits, int64_t nbr_ld, int F, int64_t h,
-                                const int32_t *h_dev, const float *Wimg, const float *bias, int M, int act, float *Y,
-                                int64_t ldY, int nsplit, int accumulate, void *stream) {
+extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *in_bias, int in_act, const void *nbr,
+                                int idx_bits, int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *Wimg,
+                                const float *bias, int M, int act, float *Y, int64_t ldY, int nsplit, int accumulate,
+                                void *stream) {
   if (!nbr) F = 1;
   EFGH_REQUIRE(efgh_bcl_conv_tc_supported(C, F, M, nsplit), "efgh_bcl_conv_tc: unsupported shape C=%d F=%d M=%d nsplit=%d", C, F, M, nsplit);
   EFGH_REQUIRE(h >= 0 && h < (1ll << 30), "efgh_bcl_conv_tc: bad h");
@@ -506,22 +626,21 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   EFGH_REQUIRE(X && Wimg && Y, "efgh_bcl_conv_tc: null pointer");
   EFGH_REQUIRE(ldX % 4 == 0 && ldY % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(in_bias) & 15) == 0,
-               "efgh_bcl_conv_tc: X, Y and Wimg must be 16-byte aligned with leading dimensions multiple of 4");
+               "efgh_bcl_conv_tc: X, Y, Wimg and in_bias must be 16-byte aligned with leading dimensions multiple of 4");
   EFGH_REQUIRE(idx_bits == 32 || idx_bits == 64, "efgh_bcl_conv_tc: idx_bits must be 32 or 64");
   ConvParams p;
-  p.trace = g_conv_trace;
+  p.trace = g_conv_trace; p.dbg_flags = g_conv_flags;
   p.X = X; p.ldX = ldX; p.C = C; p.nbr = nbr; p.nbr_ld = nbr_ld; p.F = F;
   p.h_host = (int)h; p.h_dev = h_dev; p.Wimg = Wimg; p.bias = bias; p.N = M; p.act = act; p.Y = Y; p.ldY = ldY;
   p.in_bias = in_bias; p.in_act = in_act; p.accumulate = accumulate;
   p.n_chunks = (F * C + kChunkK - 1) / kChunkK;
   p.n_groups = efgh_bcl_conv_tc_groups(F * C);
+  p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
   EFGH_REQUIRE(accumulate || p.n_groups == 1,
                "efgh_bcl_conv_tc: K=%d needs %d partial sums; call with accumulate=1 on a zero-filled Y", F * C, p.n_groups);
   size_t smem = 0;
-  p.stages = conv_tc_stages(M, F, nsplit, &smem);
-  int cols = 32;
-  while (cols < 2 * M) cols <<= 1;
-  p.tmem_cols = cols;
+  conv_tc_plan(M, nsplit, &p, &smem);
+  if ((g_conv_flags >> 4) & 15) p.raw_slots = min(p.raw_slots, (g_conv_flags >> 4) & 15);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t items = ((h + kTileM - 1) / kTileM) * p.n_groups;
   const int grid = (int)(items < sm_count() ? items : sm_count());

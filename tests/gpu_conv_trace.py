@@ -6,7 +6,8 @@ from efgh_b200 import _capi
 L = _capi.lib()
 dev = torch.device("cuda:0")
 CAP = 512
-def run(H, C, F, M, label):
+def run(H, C, F, M, label, flags=0, show=0):
+    L.efgh_debug_set_conv_flags(flags)
     X = torch.randn(H + 1, C, device=dev)
     nbr = torch.randint(-1, H, (F, H), device=dev, dtype=torch.int32) if F > 1 else None
     Wt = torch.randn(F * C, M, device=dev) * 0.1
@@ -34,8 +35,15 @@ def run(H, C, F, M, label):
             if int(t[r, i, 1]) == 0: break
             evs.append((int(t[r, i, 1]) - t0, names[r], int(t[r, i, 0])))
     evs.sort()
-    for tt, nm, ev in evs[:140]:
+    for tt, nm, ev in evs[:show]:
         print("%8.2f us  %-4s %d" % (tt / 1000.0, nm, ev))
     print("last event at %.2f us, %d events" % (evs[-1][0] / 1000.0, len(evs)))
-run(100654, 36, 15, 32, "L0 conv1")
+run(100654, 36, 15, 32, "L0 conv1 default", show=0)
+run(100654, 36, 15, 32, "L0 conv1 no-ldgsts", flags=1)
+run(62551, 36, 15, 64, "L1 conv1")
+run(23050, 68, 15, 128, "L2 conv1")
+run(4194, 132, 15, 256, "L3 conv1")
+run(885, 260, 15, 256, "L4 conv1")
 run(100654, 32, 1, 32, "L0 conv2")
+run(885, 256, 1, 256, "L4 conv2")
+L.efgh_debug_set_conv_flags(0)

@@ -54,6 +54,9 @@ constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1, kEpiWarp
 constexpr int kThreads = (kEpiWarp0 + 4) * 32;  // 704
 constexpr int kMaxRaw = 3;                   // raw-row slots per producer warp
 constexpr int kRawSlotBytes = kTeams * kTileM * 128;  // one raw slot for all teams (512 threads x 128 B)
+constexpr int kEpiRowFloats = 36;            // padded row of the epilogue staging tile (bank-conflict free)
+constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;
+constexpr int kBiasFloats = 256 + 512;       // output bias (N <= 256) + input bias (C <= 512) staged in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -216,38 +219,50 @@ __device__ __forceinline__ void group_range(int n_chunks, int n_groups, int g, i
   end = begin + base + (g < rem ? 1 : 0);
 }
 
-// Position in one producer team's chunk sequence: every item of this CTA, chunks j_begin+team, +kTeams, ...
+// Position in one producer team's chunk sequence.  The CTA's chunks (all chunks of item blockIdx.x, then of
+// item blockIdx.x + gridDim.x, ...) are numbered 0, 1, 2, ...; team t takes numbers t, t+kTeams, ...
 struct TeamPos {
   int item, j, j_end, tile;
   __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
-  __device__ __forceinline__ void settle(const ConvParams &p, int n_items, int team) {   // skip items with no chunk for this team
-    while (item < n_items) {
+  // carry j >= j_end over into the following items
+  __device__ __forceinline__ void settle(const ConvParams &p, int n_items) {
+    while (item < n_items && j >= j_end) {
+      const int over = j - j_end;
+      item += (int)gridDim.x;
+      if (item >= n_items) break;
       int jb, je;
       group_range(p.n_chunks, p.n_groups, item % p.n_groups, jb, je);
-      if (jb + team < je) { j = jb + team; j_end = je; tile = item / p.n_groups; return; }
-      item += (int)gridDim.x;
+      j = jb + over; j_end = je; tile = item / p.n_groups;
     }
   }
   __device__ __forceinline__ void init(const ConvParams &p, int n_items, int team) {
     item = (int)blockIdx.x; j = j_end = tile = 0;
-    settle(p, n_items, team);
+    if (item < n_items) {
+      int jb, je;
+      group_range(p.n_chunks, p.n_groups, item % p.n_groups, jb, je);
+      j = jb + team; j_end = je; tile = item / p.n_groups;
+      settle(p, n_items);
+    }
   }
-  __device__ __forceinline__ void advance(const ConvParams &p, int n_items, int team) {
+  __device__ __forceinline__ void advance(const ConvParams &p, int n_items) {
     j += kTeams;
-    if (j >= j_end) { item += (int)gridDim.x; settle(p, n_items, team); }
+    settle(p, n_items);
   }
 };
 
 template <typename IdxT, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [B ring: b_stages x (B_big | B_small?)] [raw ring: raw_slots x 256 threads x 128 B] [barriers]
+  // carve: [B ring: b_stages x (B_big | B_small?)] [raw ring: raw_slots x 512 threads x 128 B] [epilogue staging] [barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int N = p.N;
   const uint32_t b_bytes = (uint32_t)N * 128u * (NSPLIT == 3 ? 2 : 1);
   const uint32_t raw_base = smem_base + (uint32_t)p.b_stages * b_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes);
+  const uint32_t epi_base = raw_base + (uint32_t)p.raw_slots * kRawSlotBytes;   // 4 epilogue warps x 32 rows x 36 floats
+  float *s_bias = reinterpret_cast<float *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes + kEpiStageBytes);
+  float *s_in_bias = s_bias + 256;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + kBiasFloats);
   // barrier map (8 B each): A_full[4 teams] A_empty[4] (2 spare each) B_full[4] B_empty[4] acc_full[2] acc_empty[2]
   const uint32_t bar_a_full = smem_u32(bars), bar_a_empty = bar_a_full + 8 * 6, bar_b_full = bar_a_empty + 8 * 6,
                  bar_b_empty = bar_b_full + 8 * 4, bar_acc_full = bar_b_empty + 8 * 4, bar_acc_empty = bar_acc_full + 16;
@@ -261,6 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   constexpr uint32_t kAStageCols = NSPLIT == 3 ? 64 : 32;
   const uint32_t a_ring_col = (uint32_t)(p.acc_stages * N);
 
+  for (int i = threadIdx.x; i < N; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  if (p.in_bias)
+    for (int i = threadIdx.x; i < p.C; i += kThreads) s_in_bias[i] = __ldg(p.in_bias + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 6; ++i) { mbar_init(bar_a_full + 8 * i, 128); mbar_init(bar_a_empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
@@ -309,8 +327,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     pc = pi; pp = pi;
     int r0a, r0b, r1a, r1b, r2a, r2b;                       // row pairs for pi, pi+1, pi+2
     fetch_rows(pp, r0a, r0b);
-    pp.advance(p, n_items, team); fetch_rows(pp, r1a, r1b);
-    pp.advance(p, n_items, team); fetch_rows(pp, r2a, r2b);
+    pp.advance(p, n_items); fetch_rows(pp, r1a, r1b);
+    pp.advance(p, n_items); fetch_rows(pp, r2a, r2b);
     uint32_t n_inflight = 0, slot_i = 0, slot_c = 0, a_ph = 0;
     bool st_pending = false;
 
@@ -345,9 +363,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        pi.advance(p, n_items, team);
+        pi.advance(p, n_items);
         r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
-        pp.advance(p, n_items, team); fetch_rows(pp, r2a, r2b);
+        pp.advance(p, n_items); fetch_rows(pp, r2a, r2b);
         ++n_inflight;
         if (++slot_i == (uint32_t)p.raw_slots) slot_i = 0;
         if (tracer) trace_ev(p.trace, team, ntrace, 1);
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           for (int u = 0; u < 4; ++u) {
             int c = cb0 + 16 * hlf + 4 * u;
             if (c >= p.C) c -= p.C;
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.in_bias + c));
+            const float4 b = *reinterpret_cast<const float4 *>(s_in_bias + c);
             v[4 * u] = act_apply(v[4 * u] + b.x, p.in_act);
             v[4 * u + 1] = act_apply(v[4 * u + 1] + b.y, p.in_act);
             v[4 * u + 2] = act_apply(v[4 * u + 2] + b.z, p.in_act);
@@ -407,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       st_pending = true;
       a_ph ^= 1;
       if (tracer) trace_ev(p.trace, team, ntrace, 3);
-      pc.advance(p, n_items, team);
+      pc.advance(p, n_items);
       --n_inflight;
       if (++slot_c == (uint32_t)p.raw_slots) slot_c = 0;
     }
@@ -426,7 +444,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         for (int j = j_begin; j < j_end; ++j) {
           mbar_wait_relaxed(bar_b_empty + 8 * s, ph ^ 1);
           mbar_arrive_expect_tx(bar_b_full + 8 * s, b_bytes);
-          bulk_g2s(smem_base + s * b_bytes, reinterpret_cast<const uint8_t *>(p.Wimg) + (size_t)j * b_bytes, b_bytes, bar_b_full + 8 * s);
+          // several 8 KB copies in flight per stage: one large bulk copy is latency-bound
+          for (uint32_t off = 0; off < b_bytes; off += 8192u)
+            bulk_g2s(smem_base + s * b_bytes + off, reinterpret_cast<const uint8_t *>(p.Wimg) + (size_t)j * b_bytes + off,
+                     min(8192u, b_bytes - off), bar_b_full + 8 * s);
           if (++s == (uint32_t)p.b_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     {
       const uint32_t idesc = make_idesc(N);
-      uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0;
+      uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0, seq = 0;
       int ntrace = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
         int j_begin, j_end;
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * (uint32_t)N;
         for (int j = j_begin; j < j_end; ++j) {
-          const uint32_t team = (uint32_t)(j - j_begin) & (kTeams - 1);
+          const uint32_t team = seq++ & (kTeams - 1);
           mbar_wait(bar_a_full + 8 * team, (pha_bits >> team) & 1);
           mbar_wait(bar_b_full + 8 * sb, phb);
           tc_fence_after();
@@ -487,26 +508,62 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       mbar_wait_relaxed(bar_acc_full + 8 * as, aph);
       tc_fence_after();
       if (tracer) trace_ev(p.trace, 4, ntrace, 1);
-      const int h = tile * kTileM + q * 32 + lane;
-      float *yrow = p.Y + (int64_t)h * p.ldY;
+      // Each thread holds 32 consecutive columns of ITS row after tcgen05.ld; going straight to global memory
+      // would touch 32 rows x 16 B per instruction.  Stage the 32x32 block through shared memory so that every
+      // store / reduction instruction covers 4 rows x 128 contiguous bytes (8 lanes per row).
+      const uint32_t stage = epi_base + (uint32_t)(warp - kEpiWarp0) * (32 * kEpiRowFloats * 4);
+      const int h_warp = tile * kTileM + q * 32;
       for (int cb = 0; cb < N; cb += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)N + cb, v);
-        if (h < H && p.accumulate) {
+        if (tracer) trace_ev(p.trace, 4, ntrace, 10);
+        // bias of the 4 columns this lane will store after the transposition (one 16-byte load per block)
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.accumulate) bv = *(reinterpret_cast<const float4 *>(s_bias + cb) + (lane & 7));
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            atomicAdd(reinterpret_cast<float4 *>(yrow + cb + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        } else if (h < H) {
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * (kEpiRowFloats * 4) + (uint32_t)u * 16u),
+                       "f"(v[4 * u]), "f"(v[4 * u + 1]), "f"(v[4 * u + 2]), "f"(v[4 * u + 3])
+                       : "memory");
+        __syncwarp();
+        if (tracer) trace_ev(p.trace, 4, ntrace, 11);
+        float4 o[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o;
-            o.x = act_apply(v[i + 0] + (p.bias ? __ldg(p.bias + cb + i + 0) : 0.f), p.act);
-            o.y = act_apply(v[i + 1] + (p.bias ? __ldg(p.bias + cb + i + 1) : 0.f), p.act);
-            o.z = act_apply(v[i + 2] + (p.bias ? __ldg(p.bias + cb + i + 2) : 0.f), p.act);
-            o.w = act_apply(v[i + 3] + (p.bias ? __ldg(p.bias + cb + i + 3) : 0.f), p.act);
-            *reinterpret_cast<float4 *>(yrow + cb + i) = o;
-          }
+        for (int it8 = 0; it8 < 8; ++it8) {                   // all shared loads first, then all global stores: one warp cannot hide
+          const int row = it8 * 4 + (lane >> 3);              // the load latency of an interleaved load/store sequence
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o[it8].x), "=f"(o[it8].y), "=f"(o[it8].z), "=f"(o[it8].w)
+                       : "r"(stage + (uint32_t)row * (kEpiRowFloats * 4) + (uint32_t)(lane & 7) * 16u));
         }
+        float *ybase = p.Y + (int64_t)(h_warp + (lane >> 3)) * p.ldY + cb + 4 * (lane & 7);
+        const int h_lane = h_warp + (lane >> 3);
+        if (p.accumulate) {
+#pragma unroll
+          for (int it8 = 0; it8 < 8; ++it8)
+            if (h_lane + 4 * it8 < H) atomicAdd(reinterpret_cast<float4 *>(ybase + (int64_t)(4 * it8) * p.ldY), o[it8]);
+        } else {
+          if (p.act == 1) {
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+              o[it8].x = fmaxf(o[it8].x + bv.x, 0.f); o[it8].y = fmaxf(o[it8].y + bv.y, 0.f);
+              o[it8].z = fmaxf(o[it8].z + bv.z, 0.f); o[it8].w = fmaxf(o[it8].w + bv.w, 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int it8 = 0; it8 < 8; ++it8) {
+              o[it8].x += bv.x; o[it8].y += bv.y; o[it8].z += bv.z; o[it8].w += bv.w;
+              if (p.act == 2) {
+                o[it8].x = o[it8].x > 0.f ? o[it8].x : 0.1f * o[it8].x; o[it8].y = o[it8].y > 0.f ? o[it8].y : 0.1f * o[it8].y;
+                o[it8].z = o[it8].z > 0.f ? o[it8].z : 0.1f * o[it8].z; o[it8].w = o[it8].w > 0.f ? o[it8].w : 0.1f * o[it8].w;
+              }
+            }
+          }
+#pragma unroll
+          for (int it8 = 0; it8 < 8; ++it8)
+            if (h_lane + 4 * it8 < H) *reinterpret_cast<float4 *>(ybase + (int64_t)(4 * it8) * p.ldY) = o[it8];
+        }
+        __syncwarp();
+        if (tracer) trace_ev(p.trace, 4, ntrace, 12);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * as);
@@ -575,19 +632,19 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   const int acc_stages = 2 * N + kTeams * a_cols <= 512 ? 2 : 1;
   if (acc_stages * N + kTeams * a_cols > 512) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
-  const size_t budget = 220 * 1024 - 1024 - 256;
+  const size_t budget = 224 * 1024 - 1024 - 256 - kEpiStageBytes - kBiasFloats * 4;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
   int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
   if (raw > kMaxRaw) raw = kMaxRaw;
   if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; }
-  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + 256 + 1024;
+  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + 1024;
   return true;
 }
 
 extern "C" int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit) {
   if (!(nsplit == 1 || nsplit == 3)) return 0;
-  if (C < 32 || C % 4 != 0 || M < 32 || M > 256 || M % 32 != 0 || F < 1) return 0;
+  if (C < 32 || C > 512 || C % 4 != 0 || M < 32 || M > 256 || M % 32 != 0 || F < 1) return 0;
   return conv_tc_plan(M, nsplit, nullptr, nullptr) ? 1 : 0;
 }
 
@@ -625,7 +682,8 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   if (h == 0) return EFGH_OK;
   EFGH_REQUIRE(X && Wimg && Y, "efgh_bcl_conv_tc: null pointer");
   EFGH_REQUIRE(ldX % 4 == 0 && ldY % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(in_bias) & 15) == 0,
+                   (reinterpret_cast<uintptr_t>(Wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(in_bias) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                "efgh_bcl_conv_tc: X, Y, Wimg and in_bias must be 16-byte aligned with leading dimensions multiple of 4");
   EFGH_REQUIRE(idx_bits == 32 || idx_bits == 64, "efgh_bcl_conv_tc: idx_bits must be 32 or 64");
   ConvParams p;

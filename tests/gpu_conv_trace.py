@@ -42,8 +42,8 @@ run(100654, 36, 15, 32, "L0 conv1 default", show=0)
 run(100654, 36, 15, 32, "L0 conv1 no-ldgsts", flags=1)
 run(62551, 36, 15, 64, "L1 conv1")
 run(23050, 68, 15, 128, "L2 conv1")
-run(4194, 132, 15, 256, "L3 conv1")
+run(4194, 132, 15, 256, "L3 conv1", show=60)
 run(885, 260, 15, 256, "L4 conv1")
 run(100654, 32, 1, 32, "L0 conv2")
-run(885, 256, 1, 256, "L4 conv2")
+run(885, 256, 1, 256, "L4 conv2", show=60)
 L.efgh_debug_set_conv_flags(0)

@@ -70,7 +70,7 @@ def scatter(feat_cn, w, off, row_shift, rows, want_wsum):
     wsum = torch.zeros((rows,), dtype=torch.float32, device=feat_cn.device) if want_wsum else None
     w2, w_ld = _rows(w)
     o2, o_ld = _rows(off)
-    _capi.check(_capi.lib().efgh_bcl_scatter(feat_cn.data_ptr(), feat_cn.stride(0), feat_cn.stride(1), C, n, None,
+    _capi.check(_capi.lib().efgh_bcl_scatter(feat_cn.data_ptr(), feat_cn.stride(0), feat_cn.stride(1), C, None, 0, 0, 0, n, None,
                                              w2.data_ptr(), w_ld, o2.data_ptr(), _idx_bits(o2), o_ld, row_shift,
                                              S.data_ptr(), C, _capi.ptr(wsum), _capi.stream_ptr()),
                 "efgh_bcl_scatter")

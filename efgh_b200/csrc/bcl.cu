@@ -18,36 +18,46 @@ namespace {
 constexpr int kTP = 32;  // points per tile in scatter / gather
 
 // ---------------------------------------------------------------------------------------------
-// scatter: S[off[r,n]+shift, :] += w[r,n] * feat[:, n]
+// scatter: S[off[r,n]+shift, :] += w[r,n] * [feat ; feat2][:, n]
+// Two sources are concatenated along channels on the fly (reference nets/enet.py:113-137 materialises the
+// torch.cat); either may be channel-major (stride_n == 1) or point-major.
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT>
+template <typename IdxT, int TP>
 __global__ void __launch_bounds__(256)
-k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C, int n_host, const int32_t *n_dev,
-          const float *__restrict__ w, int64_t w_ld, const void *__restrict__ off, int64_t off_ld, int shift,
-          float *S, int64_t ldS, float *wsum) {
+k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const float *__restrict__ feat2, int64_t sc2,
+          int64_t sn2, int C2, int n_host, const int32_t *n_dev, const float *__restrict__ w, int64_t w_ld,
+          const void *__restrict__ off, int64_t off_ld, int shift, float *S, int64_t ldS, float *wsum) {
   extern __shared__ float smem[];
-  float *tile = smem;                                   // [C][kTP+1]
-  float *s_w = smem + (size_t)C * (kTP + 1);            // [4][kTP]
-  int *s_row = reinterpret_cast<int *>(s_w + 4 * kTP);  // [4][kTP]
+  const int C = C1 + C2;
+  float *tile = smem;                                   // [C][TP+1]
+  float *s_w = smem + (size_t)C * (TP + 1);             // [4][TP]
+  int *s_row = reinterpret_cast<int *>(s_w + 4 * TP);   // [4][TP]
   const int n = n_dev ? min(*n_dev, n_host) : n_host;
-  const int n_tiles = (n + kTP - 1) / kTP;
+  const int n_tiles = (n + TP - 1) / TP;
   const bool vec = (C % 4 == 0) && (ldS % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int n0 = t * kTP;
-    const int np = min(kTP, n - n0);
-    if (sn == 1) {  // channel-major (C,N): coalesce along points
-      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
-        int c = idx / kTP, p = idx % kTP;
-        tile[c * (kTP + 1) + p] = p < np ? __ldg(feat + c * sc + (n0 + p)) : 0.f;
-      }
-    } else {        // point-major: coalesce along channels
-      for (int idx = threadIdx.x; idx < C * kTP; idx += blockDim.x) {
-        int p = idx / C, c = idx % C;
-        tile[c * (kTP + 1) + p] = p < np ? __ldg(feat + c * sc + (int64_t)(n0 + p) * sn) : 0.f;
+    const int n0 = t * TP;
+    const int np = min(TP, n - n0);
+#pragma unroll
+    for (int src = 0; src < 2; ++src) {
+      const float *f = src ? feat2 : feat;
+      const int64_t fsc = src ? sc2 : sc, fsn = src ? sn2 : sn;
+      const int Cs = src ? C2 : C1, c_off = src ? C1 : 0;
+      if (Cs == 0) continue;
+      if (fsn == 1) {  // channel-major (C,N): coalesce along points
+        for (int idx = threadIdx.x; idx < Cs * TP; idx += blockDim.x) {
+          int c = idx / TP, p = idx % TP;
+          tile[(c_off + c) * (TP + 1) + p] = p < np ? __ldg(f + c * fsc + (n0 + p)) : 0.f;
+        }
+      } else {         // point-major: coalesce along channels
+        for (int idx = threadIdx.x; idx < Cs * TP; idx += blockDim.x) {
+          int p = idx / Cs, c = idx % Cs;
+          tile[(c_off + c) * (TP + 1) + p] = p < np ? __ldg(f + c * fsc + (int64_t)(n0 + p) * fsn) : 0.f;
+        }
       }
     }
-    for (int idx = threadIdx.x; idx < 4 * kTP; idx += blockDim.x) {
-      int r = idx / kTP, p = idx % kTP;
+    for (int idx = threadIdx.x; idx < 4 * TP; idx += blockDim.x) {
+      int r = idx / TP, p = idx % TP;
       bool ok = p < np;
       s_w[idx] = ok ? __ldg(w + r * w_ld + n0 + p) : 0.f;
       s_row[idx] = ok ? load_idx<IdxT>(off, r * off_ld + n0 + p) + shift : -1;
@@ -57,24 +67,24 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C, int n_h
       const int C4 = C / 4;
       for (int item = threadIdx.x; item < np * 4 * C4; item += blockDim.x) {
         const int c4 = item % C4, pr = item / C4, r = pr & 3, p = pr >> 2;
-        const int row = s_row[r * kTP + p];
+        const int row = s_row[r * TP + p];
         if (row < 0) continue;
-        const float wt = s_w[r * kTP + p];
+        const float wt = s_w[r * TP + p];
         float4 v;
-        v.x = tile[(4 * c4 + 0) * (kTP + 1) + p] * wt;
-        v.y = tile[(4 * c4 + 1) * (kTP + 1) + p] * wt;
-        v.z = tile[(4 * c4 + 2) * (kTP + 1) + p] * wt;
-        v.w = tile[(4 * c4 + 3) * (kTP + 1) + p] * wt;
+        v.x = tile[(4 * c4 + 0) * (TP + 1) + p] * wt;
+        v.y = tile[(4 * c4 + 1) * (TP + 1) + p] * wt;
+        v.z = tile[(4 * c4 + 2) * (TP + 1) + p] * wt;
+        v.w = tile[(4 * c4 + 3) * (TP + 1) + p] * wt;
         atomicAdd(reinterpret_cast<float4 *>(S + (int64_t)row * ldS) + c4, v);
         if (wsum && c4 == 0) atomicAdd(wsum + row, wt);
       }
     } else {
       for (int item = threadIdx.x; item < np * 4 * C; item += blockDim.x) {
         const int c = item % C, pr = item / C, r = pr & 3, p = pr >> 2;
-        const int row = s_row[r * kTP + p];
+        const int row = s_row[r * TP + p];
         if (row < 0) continue;
-        const float wt = s_w[r * kTP + p];
-        atomicAdd(S + (int64_t)row * ldS + c, tile[c * (kTP + 1) + p] * wt);
+        const float wt = s_w[r * TP + p];
+        atomicAdd(S + (int64_t)row * ldS + c, tile[c * (TP + 1) + p] * wt);
         if (wsum && c == 0) atomicAdd(wsum + row, wt);
       }
     }
@@ -485,23 +495,31 @@ int dispatch_idx(int idx_bits, F &&f) {
 
 using namespace efgh;
 
-extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, int64_t n,
-                                const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
-                                int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream) {
-  EFGH_REQUIRE(C > 0 && n >= 0 && n < (1ll << 30), "efgh_bcl_scatter: bad sizes C=%d n=%lld", C, (long long)n);
+extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *feat2,
+                                int64_t stride_c2, int64_t stride_n2, int C2, int64_t n, const int32_t *n_dev,
+                                const float *w, int64_t w_ld, const void *off, int idx_bits, int64_t off_ld, int row_shift,
+                                float *S, int64_t ldS, float *wsum, void *stream) {
+  if (!feat2) C2 = 0;
+  EFGH_REQUIRE(C > 0 && C2 >= 0 && n >= 0 && n < (1ll << 30), "efgh_bcl_scatter: bad sizes C=%d C2=%d n=%lld", C, C2, (long long)n);
   if (n == 0) return EFGH_OK;
   EFGH_REQUIRE(feat && w && off && S, "efgh_bcl_scatter: null pointer");
-  const size_t smem = sizeof(float) * ((size_t)C * (kTP + 1) + 4 * kTP) + sizeof(int) * 4 * kTP;
-  EFGH_REQUIRE(smem <= 200 * 1024, "efgh_bcl_scatter: C=%d too large", C);
+  // 32-point tiles when a channel-major source needs 128-byte coalescing along points; 8-point tiles otherwise
+  // (four times as many CTAs - the deep levels have few points)
+  const bool wide = C >= C2 ? stride_n == 1 : stride_n2 == 1;   // layout of the wider source decides
+  const int TP = wide ? 32 : 8;
+  const size_t smem = sizeof(float) * ((size_t)(C + C2) * (TP + 1) + 4 * TP) + sizeof(int) * 4 * TP;
+  EFGH_REQUIRE(smem <= 200 * 1024, "efgh_bcl_scatter: C=%d too large", C + C2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dispatch_idx(idx_bits, [&](auto tag) -> int {
     using IdxT = decltype(tag);
-    auto kern = k_scatter<IdxT>;
-    if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for((n + kTP - 1) / kTP, 1, 8), 256, smem, s>>>(feat, stride_c, stride_n, C, (int)n, n_dev, w, w_ld, off,
-                                                                 off_ld, row_shift, S, ldS, wsum);
-    EFGH_LAUNCH_CHECK();
-    return EFGH_OK;
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid_for((n + TP - 1) / TP, 1, 8), 256, smem, s>>>(feat, stride_c, stride_n, C, feat2, stride_c2, stride_n2, C2, (int)n,
+                                                                 n_dev, w, w_ld, off, off_ld, row_shift, S, ldS, wsum);
+      EFGH_LAUNCH_CHECK();
+      return EFGH_OK;
+    };
+    return wide ? launch(k_scatter<IdxT, 32>) : launch(k_scatter<IdxT, 8>);
   });
 }
 

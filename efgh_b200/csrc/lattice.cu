@@ -35,7 +35,7 @@ namespace {
 constexpr int kBias = 1 << 20;
 constexpr unsigned long long kEmpty = ~0ull;
 constexpr int kPointThreads = 256;
-constexpr int kTile = 512;  // points per scan tile (4 keys each)
+constexpr int kTile = 1024;  // points per scan tile (4 keys each)
 
 struct Workspace {
   unsigned long long *tkeys;
@@ -207,6 +207,8 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
     }
 
     int s4[4];
+    unsigned long long key4[4], cur4[4];
+    unsigned h4[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {                            // :106 keys[c, n, r] = greedy[c] + canonical[rank[c], r]
       int k[4];
@@ -216,16 +218,24 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
         kmin[c] = min(kmin[c], k[c]);
         kmax[c] = max(kmax[c], k[c]);
       }
-      const unsigned long long key = pack_key(k[0], k[1], k[2]);
-      unsigned h = hash_key(key) & mask;
+      key4[r] = pack_key(k[0], k[1], k[2]);
+      h4[r] = hash_key(key4[r]) & mask;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cur4[r] = tkeys[h4[r]];      // four independent probes in flight (L2 latency bound)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned long long key = key4[r];
+      unsigned h = h4[r];
+      unsigned long long cur = cur4[r];
       unsigned probes = 0;
       while (true) {
-        unsigned long long cur = tkeys[h];
         if (cur != key) {
           if (cur == kEmpty) cur = atomicCAS(&tkeys[h], kEmpty, key);
           if (cur != kEmpty && cur != key) {
             h = (h + 1) & mask;
             if (++probes > mask) { bad |= 4; break; }
+            cur = tkeys[h];
             continue;
           }
         }
@@ -254,14 +264,16 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
   if (bad) atomicOr(&st->status, (bad & 1 ? EFGH_ST_KEY_RANGE : 0) | (bad & 4 ? EFGH_ST_TABLE_FULL : 0));
 }
 
-// Single-pass scan (decoupled look-back) over first-occurrence flags; one point (4 keys) per thread.
+// Single-pass scan (decoupled look-back) over first-occurrence flags; two points (8 keys) per thread, stream
+// order preserved (thread t owns points 2t, 2t+1 of the tile).
 // status word: bits 63..62 = 1 aggregate ready / 2 inclusive prefix ready, low 32 bits = value.
-__global__ void __launch_bounds__(kTile)
+constexpr int kAssignThreads = kTile / 2;
+__global__ void __launch_bounds__(kAssignThreads)
 k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__restrict__ tmin,
          int *__restrict__ tval, const unsigned long long *__restrict__ tkeys,
          unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap) {
   __shared__ int s_tile, s_prefix;
-  __shared__ int s_warp[kTile / 32];
+  __shared__ int s_warp[kAssignThreads / 32];
   const int n = st->n;
   const int n_tiles = (n + kTile - 1) / kTile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_counter, 1);
@@ -269,17 +281,25 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__re
   const int tile = s_tile;
   if (tile >= n_tiles) return;
 
-  const int i = tile * kTile + threadIdx.x;
-  int4 s = make_int4(0, 0, 0, 0);
-  int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-  if (i < n) {
-    s = slots[i];
-    f0 = tmin[s.x] == 4 * i;
-    f1 = tmin[s.y] == 4 * i + 1;
-    f2 = tmin[s.z] == 4 * i + 2;
-    f3 = tmin[s.w] == 4 * i + 3;
+  const int i0 = tile * kTile + 2 * threadIdx.x;
+  int sl[8];
+  int fl[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int4 s = make_int4(0, 0, 0, 0);
+    if (i0 + q < n) s = slots[i0 + q];
+    sl[4 * q] = s.x; sl[4 * q + 1] = s.y; sl[4 * q + 2] = s.z; sl[4 * q + 3] = s.w;
   }
-  const int cnt = f0 + f1 + f2 + f3;
+  int mins[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mins[e] = (i0 + (e >> 2) < n) ? tmin[sl[e]] : -1;   // eight independent L2 reads in flight
+  int cnt = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { fl[e] = mins[e] == 4 * (i0 + (e >> 2)) + (e & 3); cnt += fl[e]; }
+  unsigned long long kk[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) kk[e] = fl[e] ? tkeys[sl[e]] : 0ull;                 // keys of the first occurrences, fetched early
+
   // block exclusive scan of cnt
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = cnt;
@@ -291,45 +311,55 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__re
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    int v = lane < kTile / 32 ? s_warp[lane] : 0;
+    int v = lane < kAssignThreads / 32 ? s_warp[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, v, o);
       if (lane >= o) v += t;
     }
-    if (lane < kTile / 32) s_warp[lane] = v;  // inclusive warp totals
+    if (lane < kAssignThreads / 32) s_warp[lane] = v;  // inclusive warp totals
   }
   __syncthreads();
-  const int block_total = s_warp[kTile / 32 - 1];
+  const int block_total = s_warp[kAssignThreads / 32 - 1];
   const int local = inc - cnt + (wid ? s_warp[wid - 1] : 0);
 
-  if (threadIdx.x == 0) {
-    int prefix = 0;
+  if (wid == 0) {
+    // warp-parallel look-back: lane l inspects tile (base - l); stop at the first inclusive prefix
     volatile unsigned long long *vt = tiles;
+    int prefix = 0;
     if (tile > 0) {
-      vt[tile] = (1ull << 62) | (unsigned)block_total;
-      for (int j = tile - 1; j >= 0; --j) {
-        unsigned long long w;
-        do { w = vt[j]; } while ((w >> 62) == 0);
-        prefix += (int)(unsigned)(w & 0xffffffffu);
-        if ((w >> 62) == 2) break;
+      if (lane == 0) vt[tile] = (1ull << 62) | (unsigned)block_total;
+      int base = tile - 1;
+      while (true) {
+        const int j = base - lane;
+        unsigned long long w = 2ull << 62;                 // virtual tile before tile 0: inclusive prefix 0
+        if (j >= 0) { do { w = vt[j]; } while ((w >> 62) == 0); }
+        const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const int first = __ffs(incl) - 1;                  // nearest tile that already knows its inclusive prefix
+        int contrib = (first < 0 || lane <= first) ? (int)(unsigned)(w & 0xffffffffu) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        prefix += contrib;
+        if (first >= 0) break;
+        base -= 32;
       }
     }
-    __threadfence();
-    vt[tile] = (2ull << 62) | (unsigned)(prefix + block_total);
-    s_prefix = prefix;
-    if (tile == n_tiles - 1) {
-      const int total = prefix + block_total;
-      st->hash_cnt = total;
-      if (total > h_cap) atomicOr(&st->status, EFGH_ST_VERTEX_CAP);
+    if (lane == 0) {
+      __threadfence();
+      vt[tile] = (2ull << 62) | (unsigned)(prefix + block_total);
+      s_prefix = prefix;
+      if (tile == n_tiles - 1) {
+        const int total = prefix + block_total;
+        st->hash_cnt = total;
+        if (total > h_cap) atomicOr(&st->status, EFGH_ST_VERTEX_CAP);
+      }
     }
   }
   __syncthreads();
   int idx = s_prefix + local;
-  if (f0) { tval[s.x] = idx; vkeys[idx] = tkeys[s.x]; ++idx; }
-  if (f1) { tval[s.y] = idx; vkeys[idx] = tkeys[s.y]; ++idx; }
-  if (f2) { tval[s.z] = idx; vkeys[idx] = tkeys[s.z]; ++idx; }
-  if (f3) { tval[s.w] = idx; vkeys[idx] = tkeys[s.w]; ++idx; }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (fl[e]) { tval[sl[e]] = idx; vkeys[idx] = kk[e]; ++idx; }
 }
 
 __device__ __forceinline__ int table_find(const unsigned long long *__restrict__ tkeys,
@@ -384,41 +414,46 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
                          {0.0f, EFGH_E_B2, EFGH_E_C},
                          {0.0f, 0.0f, EFGH_E_C3}};
 
-  for (int h = tid; h < H; h += stride) {
+  // One (filter tap, vertex) pair per thread, vertex fastest: a thread does ONE dependent table probe instead of
+  // F of them in sequence (the probes are L2-latency bound), and stores to nbr[f, :] stay coalesced.
+  const bool want_nbr = F > 0 && (nbr || nbr32);
+  const int taps = want_nbr ? F : 1;
+  const long long total = (long long)taps * H;
+  for (long long item = tid; item < total; item += stride) {
+    const int f = (int)(item / H);
+    const int h = (int)(item - (long long)f * H);
     int k[4];
     unpack_key(vkeys[h], k[0], k[1], k[2]);
     k[3] = -(k[0] + k[1] + k[2]);
-    if (F > 0 && (nbr || nbr32)) {
-      for (int f = 0; f < F; ++f) {
-        const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
-        int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
-        bool in_box = true;
+    if (want_nbr) {
+      const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
+      int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
+      bool in_box = true;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) in_box = in_box && q[c] >= kmin[c] && q[c] <= kmax[c];
-        int res;
-        if (in_box) {
-          res = (q[0] + q[1] + q[2] + q[3] == 0) ? table_find(tkeys, tval, mask, pack_key(q[0], q[1], q[2])) : -1;
-        } else {
-          // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
-          // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
-          const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
-                          s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
-          long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
-                        (q[3] - kmin[3]);
-          res = -1;
-          if (P >= 0 && P < s0 * s1 * s2 * s3) {
-            const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
-            const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
-            const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
-            const int r0 = (int)P + kmin[0], r1 = (int)a1 + kmin[1], r2 = (int)a2 + kmin[2], r3 = (int)a3 + kmin[3];
-            if (r0 + r1 + r2 + r3 == 0) res = table_find(tkeys, tval, mask, pack_key(r0, r1, r2));
-          }
+      for (int c = 0; c < 4; ++c) in_box = in_box && q[c] >= kmin[c] && q[c] <= kmax[c];
+      int res;
+      if (in_box) {
+        res = (q[0] + q[1] + q[2] + q[3] == 0) ? table_find(tkeys, tval, mask, pack_key(q[0], q[1], q[2])) : -1;
+      } else {
+        // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
+        // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
+        const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
+                        s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
+        long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
+                      (q[3] - kmin[3]);
+        res = -1;
+        if (P >= 0 && P < s0 * s1 * s2 * s3) {
+          const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
+          const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
+          const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
+          const int r0 = (int)P + kmin[0], r1 = (int)a1 + kmin[1], r2 = (int)a2 + kmin[2], r3 = (int)a3 + kmin[3];
+          if (r0 + r1 + r2 + r3 == 0) res = table_find(tkeys, tval, mask, pack_key(r0, r1, r2));
         }
-        if (nbr) nbr[f * nbr_ld + h] = res;
-        if (nbr32) nbr32[f * nbr_ld + h] = res;
       }
+      if (nbr) nbr[f * nbr_ld + h] = res;
+      if (nbr32) nbr32[f * nbr_ld + h] = res;
     }
-    if (next_pts) {                                          // generate_data.py:177-178
+    if (next_pts && f == 0) {                                // generate_data.py:177-178
       float q[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) q[c] = __fdiv_rn((float)k[c], next_divisor);
@@ -463,7 +498,7 @@ extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, 
   k_points<<<grid_for(n, kPointThreads, 8), kPointThreads, 0, s>>>(pts, pts_ld, scale, barycentric, el_minus_gr,
                                                                    out_ld, state, w.tkeys, w.tmin, w.slots);
   EFGH_LAUNCH_CHECK();
-  k_assign<<<(int)((n + kTile - 1) / kTile), kTile, 0, s>>>(state, w.slots, w.tmin, w.tval, w.tkeys, w.vkeys, w.tiles,
+  k_assign<<<(int)((n + kTile - 1) / kTile), kAssignThreads, 0, s>>>(state, w.slots, w.tmin, w.tval, w.tkeys, w.vkeys, w.tiles,
                                                             (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30)));
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
@@ -487,7 +522,8 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
   }
   if (n == 0) return EFGH_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t items = n > h ? n : h;
+  const int64_t vitems = h * (F > 0 ? F : 1);
+  const int64_t items = n > vitems ? n : vitems;
   k_vertices<<<grid_for(items, 256, 8), 256, 0, s>>>(state, (int)n, (int)h, w.slots, w.tval, w.tkeys, w.vkeys,
                                                      lattice_offset, lattice_offset32, off_ld, filter_offsets, F,
                                                      blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,

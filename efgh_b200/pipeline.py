@@ -101,7 +101,7 @@ class ScanPipeline(object):
             self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
-        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 2 + 1 + 2) + sum(1 for lv in self.levels if lv.get("split0"))
+        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 1 + 2) + sum(1 for lv in self.levels if lv.get("split0"))
 
     # ------------------------------------------------------------------------------------------
     def enqueue(self, pc, feat0, stream=None, timers=None):
@@ -143,11 +143,10 @@ class ScanPipeline(object):
                                               "efgh_bcl_zero"))
 
             def splat():
-                ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, n_cap, n_dev, lv["bary"].data_ptr(), n_cap,
-                                      lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
+                # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat
+                ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev,
+                                      lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
                                       lv["wsum"].data_ptr() if self.use_norm else None, s), "efgh_bcl_scatter")
-                ck(L.efgh_bcl_scatter(prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev, lv["bary"].data_ptr(), n_cap,
-                                      lv["loff32"].data_ptr(), 32, n_cap, 1, S + 16, cin, None, s), "efgh_bcl_scatter")
                 if self.use_norm:
                     ck(L.efgh_bcl_normalize(S, cin, cin, lv["wsum"].data_ptr(), None, h_cap + 1, h_dev, 1, s),
                        "efgh_bcl_normalize")

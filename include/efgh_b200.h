@@ -119,11 +119,14 @@ int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, int64_t rows_cap, c
                   int rows_extra, void *stream);
 
 /* Splat (bilateralNN.py:176-191) and its density normaliser (:193-211); also the adjoint of slice.
- *   S[(off[r,n]+row_shift), c] += w[r,n] * feat[c,n];  wsum[(off[r,n]+row_shift)] += w[r,n] (if wsum)
- *   S is (rows, C) with leading dimension ldS; the caller zero-fills S and wsum beforehand. */
-int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, int64_t n,
-                     const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
-                     int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream);
+ *   S[(off[r,n]+row_shift), c] += w[r,n] * X[c,n];  wsum[(off[r,n]+row_shift)] += w[r,n] (if wsum)
+ *   X = [feat ; feat2] concatenated along channels on the fly (feat2 may be NULL): E-Net feeds every BCL
+ *   torch.cat((el_minus_gr, previous output)) (reference nets/enet.py:113-137), which is never materialised.
+ *   S is (rows, C + C2) with leading dimension ldS; the caller zero-fills S and wsum beforehand. */
+int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *feat2,
+                     int64_t stride_c2, int64_t stride_n2, int C2, int64_t n, const int32_t *n_dev, const float *w,
+                     int64_t w_ld, const void *off, int idx_bits, int64_t off_ld, int row_shift, float *S, int64_t ldS,
+                     float *wsum, void *stream);
 
 /* inv[r] = 1 / (wsum[r] + 1e-5)   (bilateralNN.py:210) for r < rows (rows_dev + rows_extra if given) */
 int efgh_bcl_inv_norm(const float *wsum, float *inv, int64_t rows, const int32_t *rows_dev, int rows_extra,

@@ -21,7 +21,7 @@ SIGNATURES = {
     "efgh_lattice_points": (i32, [vp, i64, i64, vp, f32, vp, vp, i64, i64, vp, vp, sz, vp]),
     "efgh_lattice_vertices": (i32, [i64, vp, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, f32, vp, vp, sz, vp]),
     "efgh_bcl_scatter": (i32, [vp, i64, i64, i32, vp, i64, i64, i32, i64, vp, vp, i64, vp, i32, i64, i32, vp, i64, vp, vp]),
-    "efgh_bcl_zero": (i32, [vp, i64, i32, vp, i64, vp, i32, vp]),
+    "efgh_bcl_zero": (i32, [vp, i64, i32, vp, vp, i64, i32, i64, vp, i32, vp]),
     "efgh_bcl_inv_norm": (i32, [vp, vp, i64, vp, i32, vp]),
     "efgh_bcl_gather": (i32, [vp, i64, i32, vp, i64, vp, vp, i64, vp, i32, i64, i32, vp, vp, i64, i64, vp]),
     "efgh_bcl_conv": (i32, [vp, i64, i32, vp, vp, i32, i64, i32, i64, vp, vp, vp, i32, i32, vp, i64, i32, vp]),

@@ -92,20 +92,28 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const 
   }
 }
 
-__global__ void k_zero(float *__restrict__ S, int64_t ldS, int C, float *__restrict__ wsum, int rows_host,
-                       const int32_t *rows_dev, int rows_extra) {
-  const int rows = rows_dev ? min(*rows_dev + rows_extra, rows_host) : rows_host;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ldS == C && C % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
-    float4 *S4 = reinterpret_cast<float4 *>(S);
+__device__ __forceinline__ void zero_rows(float *__restrict__ M, int64_t ld, int C, int rows, int64_t tid, int64_t stride) {
+  if (ld == C && C % 4 == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0) {
+    float4 *M4 = reinterpret_cast<float4 *>(M);
     const int64_t total = (int64_t)rows * C / 4;
-    for (int64_t i = tid; i < total; i += stride) S4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = tid; i < total; i += stride) M4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     const int64_t total = (int64_t)rows * C;
-    for (int64_t i = tid; i < total; i += stride) S[(i / C) * ldS + (i % C)] = 0.f;
+    for (int64_t i = tid; i < total; i += stride) M[(i / C) * ld + (i % C)] = 0.f;
   }
+}
+
+// One launch zero-fills everything a BCL forward accumulates into: the splat matrix S and density sums (rows + extra)
+// and, optionally, the convolution's split-K accumulator Y2 (rows).
+__global__ void k_zero(float *__restrict__ S, int64_t ldS, int C, float *__restrict__ wsum, float *__restrict__ Y2,
+                       int64_t ldY2, int C2, int rows_host, const int32_t *rows_dev, int rows_extra) {
+  const int base = rows_dev ? min(*rows_dev, rows_host) : rows_host;
+  const int rows = rows_dev ? min(base + rows_extra, rows_host + rows_extra) : rows_host + rows_extra;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (S) zero_rows(S, ldS, C, rows, tid, stride);
   if (wsum)
     for (int64_t i = tid; i < rows; i += stride) wsum[i] = 0.f;
+  if (Y2) zero_rows(Y2, ldY2, C2, base, tid, stride);
 }
 
 __global__ void k_normalize(float *__restrict__ S, int64_t ldS, int C, const float *__restrict__ wsum,
@@ -523,13 +531,15 @@ extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t str
   });
 }
 
-extern "C" int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, int64_t rows_cap, const int32_t *rows_dev,
-                             int rows_extra, void *stream) {
-  EFGH_REQUIRE(C > 0 && ldS >= C && rows_cap >= 0 && rows_cap < (1ll << 31), "efgh_bcl_zero: bad sizes");
-  if (rows_cap == 0) return EFGH_OK;
-  EFGH_REQUIRE(S, "efgh_bcl_zero: null pointer");
-  k_zero<<<grid_for(rows_cap * C / 4, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ldS, C, wsum, (int)rows_cap,
-                                                                                         rows_dev, rows_extra);
+extern "C" int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, float *Y2, int64_t ldY2, int C2, int64_t rows,
+                             const int32_t *rows_dev, int rows_extra, void *stream) {
+  EFGH_REQUIRE(rows >= 0 && rows < (1ll << 31) && rows_extra >= 0, "efgh_bcl_zero: bad sizes");
+  EFGH_REQUIRE(!S || (C > 0 && ldS >= C), "efgh_bcl_zero: bad S shape");
+  EFGH_REQUIRE(!Y2 || (C2 > 0 && ldY2 >= C2), "efgh_bcl_zero: bad Y2 shape");
+  if (rows + rows_extra == 0 || (!S && !wsum && !Y2)) return EFGH_OK;
+  const int64_t work = (rows + rows_extra) * (int64_t)((S ? C : 1) + (Y2 ? C2 : 0)) / 4;
+  k_zero<<<grid_for(work, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ldS, C, wsum, Y2, ldY2, C2, (int)rows, rows_dev,
+                                                                               rows_extra);
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
 }

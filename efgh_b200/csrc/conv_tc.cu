@@ -33,7 +33,7 @@
 // lattices of the deep levels.  Work item = (128-vertex tile, K group); persistent CTAs, one per SM,
 // stride over the items; the vertex count is read from device memory.
 //
-// TMEM map (512 columns): [accumulators: acc_stages x N] [A operand: 4 teams x (32 big | 32 small)].
+// TMEM map (512 columns): [accumulators: acc_stages x nacc x N] [A operand: 4 teams x (32 big | 32 small)].
 #include "common.cuh"
 
 static unsigned long long *g_conv_trace = nullptr;
@@ -74,11 +74,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra LAB_DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend-time hint: sleep in hardware instead of
+      "@p bra LAB_DONE;\n\t"                                            // spinning - a spinning warp steals issue slots from
+      "bra LAB_WAIT;\n\t"                                               // the one producer warp per scheduler that has work
       "LAB_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "}" ::"r"(bar), "r"(parity), "r"(20000u)
       : "memory");
 }
 // Same, but yields issue slots between polls: used by roles whose wake-up latency is not critical (their
@@ -89,11 +89,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
     __nanosleep(64);
@@ -207,7 +207,7 @@ struct ConvParams {
   const float *Wimg; const float *bias; int N; int act;
   float *Y; int64_t ldY;
   int n_chunks; int n_groups;
-  int b_stages, raw_slots, acc_stages;
+  int b_stages, raw_slots, acc_stages, nacc;   // nacc: independent accumulators per stage (see the MMA issuer)
   uint32_t magic_c;                     // ceil(2^32 / C): k / C == __umulhi(k, magic_c) for the k range used here
   int accumulate;                       // 1: red.add raw partial sums into pre-zeroed Y (bias/act deferred); 0: store act(bias + acc)
 };
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   const int n_items = n_tiles * p.n_groups;
   const int K = p.F * p.C;
   constexpr uint32_t kAStageCols = NSPLIT == 3 ? 64 : 32;
-  const uint32_t a_ring_col = (uint32_t)(p.acc_stages * N);
+  const uint32_t a_ring_col = (uint32_t)(p.acc_stages * p.nacc * N);
 
   for (int i = threadIdx.x; i < N; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   if (p.in_bias)
@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     const bool tracer = r == 0 && team < 2;
     int ntrace = 0;
 
-    // neighbour rows (taps f, f+1) of this thread's vertex for the chunk at `pos`; -1 = absent -> zeros
+    // RAW neighbour indices (taps f, f+1) of this thread's vertex for the chunk at `pos`.  The loaded values are not
+    // touched here - any arithmetic on them would stall this in-order warp for the full L2 latency; they are decoded
+    // (+1, sink test) two chunks later, when they are used.  Encoding: with a neighbour table, raw = nbr (-1 = absent);
+    // without one (1x1 convolution), raw = own row or -1.
     auto fetch_rows = [&](const TeamPos &pos, int &ra, int &rb) {
       ra = rb = -1;
       if (!pos.valid(n_items)) return;
@@ -314,13 +317,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       if (h >= H) return;
       if (!p.nbr) { ra = h; return; }
       const int f = (int)__umulhi((uint32_t)(pos.j * kChunkK), p.magic_c);
-      const int a = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h) + 1;
-      ra = a == 0 ? -1 : a;                                                   // sink row: all zeros
-      if (f + 1 < p.F) {
-        const int b = load_idx<IdxT>(p.nbr, (f + 1) * p.nbr_ld + h) + 1;
-        rb = b == 0 ? -1 : b;
-      }
+      ra = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h);
+      if (f + 1 < p.F) rb = load_idx<IdxT>(p.nbr, (f + 1) * p.nbr_ld + h);
     };
+    const int row_bias = p.nbr ? 1 : 0;                       // raw index -> matrix row (row 0 of a sink matrix = absent)
 
     TeamPos pi, pc, pp;                                     // issue / convert / row-prefetch positions
     pi.init(p, n_items, team);
@@ -348,14 +348,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         for (int i = 0; i < 8; ++i) {                         // all shuffles first: they pipeline
           const int R = 4 * i + (lane >> 3);
           const int ra = __shfl_sync(0xffffffffu, r0a, R), rb = __shfl_sync(0xffffffffu, r0b, R);
-          rows[i] = in_k ? (wrap ? rb : ra) : -1;
+          rows[i] = in_k ? (wrap ? rb : ra) : -1;               // raw; row = raw + row_bias, valid iff raw >= 0
         }
+        if (tracer) trace_ev(p.trace, team, ntrace, 5);
         const uint32_t dst_lane = dst + ((uint32_t)lane >> 3) * 128u;
         const uint32_t u_lane = (uint32_t)lane & 7u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t R7 = ((uint32_t)(4 * i) + ((uint32_t)lane >> 3)) & 7u;
-          const float *src = rows[i] >= 0 ? p.X + (int64_t)rows[i] * p.ldX + c_u : p.X;
+          const float *src = rows[i] >= 0 ? p.X + (int64_t)(rows[i] + row_bias) * p.ldX + c_u : p.X;
           const uint32_t nbytes = rows[i] >= 0 ? 16u : 0u;
           if (!(p.dbg_flags & 1))
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_lane + (uint32_t)i * 512u + ((u_lane ^ R7) << 4)), "l"(src),
@@ -363,8 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tracer) trace_ev(p.trace, team, ntrace, 6);
         pi.advance(p, n_items);
         r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
+        if (tracer) trace_ev(p.trace, team, ntrace, 7);
         pp.advance(p, n_items); fetch_rows(pp, r2a, r2b);
         ++n_inflight;
         if (++slot_i == (uint32_t)p.raw_slots) slot_i = 0;
@@ -455,6 +458,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     {
+      // shfl-broadcast marks the value warp-uniform for ptxas, so descriptors and TMEM addresses are computed in the
+      // uniform datapath instead of costing an R2UR per operand per MMA
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
       const uint32_t idesc = make_idesc(N);
       uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0, seq = 0;
       int ntrace = 0;
@@ -466,28 +472,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
         mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);      // epilogue drained this accumulator stage
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (uint32_t)N;
+        // When TMEM has room the three products of 3xTF32 go to separate accumulators that the epilogue adds up with
+        // round-to-nearest adds: d_sb (A_small*B_big), d_bs (A_big*B_small), d_bb (A_big*B_big).  The tensor core
+        // rounds toward zero on every accumulate, so keeping the tiny correction products out of the main chain
+        // shortens it 3x (measured error 1.0e-6 instead of 1.7e-6 per layer).
+        const uint32_t tmem_d0 = tmem_base + as * (uint32_t)(p.nacc * N);
+        const uint32_t d_bb = tmem_d0 + (uint32_t)((p.nacc - 1) * N);
+        const uint32_t d_sb = tmem_d0, d_bs = tmem_d0 + (uint32_t)((p.nacc == 3 ? 1 : 0) * N);
         for (int j = j_begin; j < j_end; ++j) {
           const uint32_t team = seq++ & (kTeams - 1);
           mbar_wait(bar_a_full + 8 * team, (pha_bits >> team) & 1);
+          if (lane == 0) trace_ev(p.trace, 3, ntrace, 1);
           mbar_wait(bar_b_full + 8 * sb, phb);
           tc_fence_after();
           if (lane == 0) trace_ev(p.trace, 3, ntrace, 2);
           const uint32_t a_big = tmem_base + a_ring_col + team * kAStageCols, a_small = a_big + 32;
           const uint32_t b_big = smem_base + sb * b_bytes, b_small = b_big + (uint32_t)N * 128u;
           const uint64_t dbb = make_desc(b_big);
-          uint32_t acc = j > j_begin;
+          const uint32_t first = j == j_begin;
           if (NSPLIT == 3) {
             const uint64_t dbs = make_desc(b_small);
+            // interleave the chains so that back-to-back MMAs never target the same accumulator
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) { umma_tf32_ts(tmem_d, a_small + 8 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ts(d_sb, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
+              umma_tf32_ts(d_bs, a_big + 8 * k4, dbs + 2 * k4, idesc, !(first && k4 == 0 && p.nacc == 3));
+              umma_tf32_ts(d_bb, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0 && p.nacc >= 2));
+            }
+          } else {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(tmem_d, a_big + 8 * k4, dbs + 2 * k4, idesc, 1);
+            for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(d_bb, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
           }
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) { umma_tf32_ts(tmem_d, a_big + 8 * k4, dbb + 2 * k4, idesc, acc); acc = 1; }
           umma_commit(bar_a_empty + 8 * team);               // frees the team's TMEM A stage when these MMAs retire
           umma_commit(bar_b_empty + 8 * sb);                 // ... and the weight stage
+          if (lane == 0) trace_ev(p.trace, 3, ntrace, 3);
           pha_bits ^= 1u << team;
           if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1; }
         }
@@ -515,7 +533,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       const int h_warp = tile * kTileM + q * 32;
       for (int cb = 0; cb < N; cb += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)N + cb, v);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(p.nacc * N) + cb;
+        tmem_ld32(tacc, v);
+        for (int d = 1; d < p.nacc; ++d) {                    // add the independent partial accumulators (round-to-nearest adds)
+          float w[32];
+          tmem_ld32(tacc + (uint32_t)(d * N), w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
         if (tracer) trace_ev(p.trace, 4, ntrace, 10);
         // bias of the 4 columns this lane will store after the transposition (one 16-byte load per block)
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -629,15 +654,21 @@ extern "C" int efgh_bcl_bias_act(float *Y, int64_t ldY, int M, int64_t h, const 
 // shared memory = b_stages weight tiles + raw_slots x 64 KB of warp-private row slots.
 static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   const int a_cols = nsplit == 3 ? 64 : 32;
-  const int acc_stages = 2 * N + kTeams * a_cols <= 512 ? 2 : 1;
-  if (acc_stages * N + kTeams * a_cols > 512) return false;
+  const int room = 512 - kTeams * a_cols;                // TMEM columns left for accumulators
+  int nacc = 1, acc_stages = 1;
+  // two accumulator stages first (epilogue of item i overlaps the MMAs of item i+1), then spare columns go to
+  // separate accumulators for the 3xTF32 correction products (shorter chains, smaller rounding error)
+  if (nsplit == 3 && 6 * N <= room) { nacc = 3; acc_stages = 2; }
+  else if (nsplit == 3 && 4 * N <= room) { nacc = 2; acc_stages = 2; }
+  else if (2 * N <= room) { nacc = 1; acc_stages = 2; }
+  if (acc_stages * nacc * N > room) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
   const size_t budget = 224 * 1024 - 1024 - 256 - kEpiStageBytes - kBiasFloats * 4;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
   int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
   if (raw > kMaxRaw) raw = kMaxRaw;
-  if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; }
+  if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; p->nacc = nacc; }
   if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + 1024;
   return true;
 }

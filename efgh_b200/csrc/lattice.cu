@@ -12,9 +12,9 @@
 //              (generate_data.py:175-178)
 //
 // Data layout in HBM (all sized by the caller through efgh_lattice_workspace_bytes):
-//   tkeys  u64[T]   packed key per table slot (3 coordinates x 21 bits; the 4th is minus their sum)
-//   tmin   i32[T]   smallest stream position that inserted the key
-//   tval   i32[T]   vertex index of the key (valid after k_assign)
+//   table  {u64 key, i32 first_pos, i32 index}[T]  16-byte entries: packed key (3 coordinates x 21 bits; the 4th
+//                   is minus their sum), smallest stream position that inserted it, vertex index (valid after
+//                   k_assign) - one 16-byte load per probe returns everything a later pass needs
 //   slots  int4[n]  table slot of each of the point's 4 keys (so later passes never re-probe)
 //   vkeys  u64[4n]  packed key of vertex h, insertion order
 //   tiles  u64[..]  look-back status words
@@ -37,10 +37,14 @@ constexpr unsigned long long kEmpty = ~0ull;
 constexpr int kPointThreads = 256;
 constexpr int kTile = 1024;  // points per scan tile (4 keys each)
 
+struct __align__(16) Entry {
+  unsigned long long key;
+  int first_pos;
+  int index;
+};
+
 struct Workspace {
-  unsigned long long *tkeys;
-  int *tmin;
-  int *tval;
+  Entry *table;
   int4 *slots;
   unsigned long long *vkeys;
   unsigned long long *tiles;
@@ -62,9 +66,7 @@ Workspace carve(void *base, int64_t n_cap) {
   w.table_cap = pow2_ceil(8 * n_cap);
   size_t off = 0;
   char *b = static_cast<char *>(base);
-  w.tkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * w.table_cap);
-  w.tmin = reinterpret_cast<int *>(b + off); off = align_up(off + sizeof(int) * w.table_cap);
-  w.tval = reinterpret_cast<int *>(b + off); off = align_up(off + sizeof(int) * w.table_cap);
+  w.table = reinterpret_cast<Entry *>(b + off); off = align_up(off + sizeof(Entry) * w.table_cap);
   w.slots = reinterpret_cast<int4 *>(b + off); off = align_up(off + sizeof(int4) * n_cap);
   w.vkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * 4 * n_cap);
   w.tiles = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * ((n_cap + kTile - 1) / kTile + 1));
@@ -101,15 +103,13 @@ __device__ __forceinline__ int table_mask_for(int n, int64_t table_cap) {
 }
 
 __global__ void k_clear(efgh_lattice_state *st, const int32_t *n_dev, int n_host, int64_t table_cap,
-                        unsigned long long *tkeys, int *tmin, unsigned long long *tiles, int n_tiles_cap) {
+                        Entry *table, unsigned long long *tiles, int n_tiles_cap) {
   int n = n_dev ? min(max(*n_dev, 0), n_host) : n_host;
   int mask = table_mask_for(n, table_cap);
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = tid; i <= mask; i += stride) {
-    tkeys[i] = kEmpty;
-    tmin[i] = 0x7fffffff;
-  }
+  const int4 empty = make_int4(-1, -1, 0x7fffffff, -1);   // key = ~0, first_pos = INT_MAX, index = -1
+  for (int64_t i = tid; i <= mask; i += stride) reinterpret_cast<int4 *>(table)[i] = empty;
   int n_tiles = (n + kTile - 1) / kTile;
   for (int64_t i = tid; i < n_tiles && i < n_tiles_cap; i += stride) tiles[i] = 0ull;
   if (tid == 0) {
@@ -138,8 +138,7 @@ __device__ __forceinline__ int canonical(int i, int j) { return (j <= 3 - i) ? j
 
 __global__ void __launch_bounds__(kPointThreads)
 k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__restrict__ bary,
-         float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, unsigned long long *tkeys,
-         int *tmin, int4 *slots) {
+         float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, Entry *table, int4 *slots) {
   const int n = st->n;
   const unsigned mask = (unsigned)st->table_mask;
   int kmin[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
@@ -222,26 +221,23 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
       h4[r] = hash_key(key4[r]) & mask;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) cur4[r] = tkeys[h4[r]];      // four independent probes in flight (L2 latency bound)
+    for (int r = 0; r < 4; ++r) cur4[r] = table[h4[r]].key;   // four independent probes in flight (L2 latency bound)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)                                // ... and four independent claims of empty slots
+      if (cur4[r] == kEmpty) cur4[r] = atomicCAS(&table[h4[r]].key, kEmpty, key4[r]);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const unsigned long long key = key4[r];
       unsigned h = h4[r];
-      unsigned long long cur = cur4[r];
+      unsigned long long cur = cur4[r];                        // kEmpty here means "we just claimed it"
       unsigned probes = 0;
-      while (true) {
-        if (cur != key) {
-          if (cur == kEmpty) cur = atomicCAS(&tkeys[h], kEmpty, key);
-          if (cur != kEmpty && cur != key) {
-            h = (h + 1) & mask;
-            if (++probes > mask) { bad |= 4; break; }
-            cur = tkeys[h];
-            continue;
-          }
-        }
-        break;
+      while (cur != kEmpty && cur != key) {                    // collision: linear probing
+        h = (h + 1) & mask;
+        if (++probes > mask) { bad |= 4; break; }
+        cur = table[h].key;
+        if (cur == kEmpty) cur = atomicCAS(&table[h].key, kEmpty, key);
       }
-      atomicMin(&tmin[h], 4 * i + r);
+      atomicMin(&table[h].first_pos, 4 * i + r);
       s4[r] = (int)h;
     }
     slots[i] = make_int4(s4[0], s4[1], s4[2], s4[3]);
@@ -259,7 +255,13 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
   if (threadIdx.x < 4) {
     int c = threadIdx.x, mn = s_min[c][0], mx = s_max[c][0];
     for (int w = 1; w < kPointThreads / 32; ++w) { mn = min(mn, s_min[c][w]); mx = max(mx, s_max[c][w]); }
-    if (mn <= mx) { atomicMin(&st->key_min[c], mn); atomicMax(&st->key_max[c], mx); }
+    // The 8 box words share one 32-byte sector, so every atomic on them serialises in one L2 slice; only CTAs that
+    // actually widen the box issue one (the plain read may be stale, but the box only ever widens - a stale value
+    // just costs a redundant atomic).
+    if (mn <= mx) {
+      if (mn < *(volatile int *)&st->key_min[c]) atomicMin(&st->key_min[c], mn);
+      if (mx > *(volatile int *)&st->key_max[c]) atomicMax(&st->key_max[c], mx);
+    }
   }
   if (bad) atomicOr(&st->status, (bad & 1 ? EFGH_ST_KEY_RANGE : 0) | (bad & 4 ? EFGH_ST_TABLE_FULL : 0));
 }
@@ -269,8 +271,7 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
 // status word: bits 63..62 = 1 aggregate ready / 2 inclusive prefix ready, low 32 bits = value.
 constexpr int kAssignThreads = kTile / 2;
 __global__ void __launch_bounds__(kAssignThreads)
-k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__restrict__ tmin,
-         int *__restrict__ tval, const unsigned long long *__restrict__ tkeys,
+k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
          unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap) {
   __shared__ int s_tile, s_prefix;
   __shared__ int s_warp[kAssignThreads / 32];
@@ -290,15 +291,20 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__re
     if (i0 + q < n) s = slots[i0 + q];
     sl[4 * q] = s.x; sl[4 * q + 1] = s.y; sl[4 * q + 2] = s.z; sl[4 * q + 3] = s.w;
   }
-  int mins[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) mins[e] = (i0 + (e >> 2) < n) ? tmin[sl[e]] : -1;   // eight independent L2 reads in flight
-  int cnt = 0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { fl[e] = mins[e] == 4 * (i0 + (e >> 2)) + (e & 3); cnt += fl[e]; }
   unsigned long long kk[8];
+  int cnt = 0;
+  {
+    int4 ent[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) kk[e] = fl[e] ? tkeys[sl[e]] : 0ull;                 // keys of the first occurrences, fetched early
+    for (int e = 0; e < 8; ++e)                                                    // eight independent 16-byte L2 reads in flight
+      ent[e] = (i0 + (e >> 2) < n) ? *reinterpret_cast<const int4 *>(table + sl[e]) : make_int4(0, 0, -1, 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      fl[e] = ent[e].z == 4 * (i0 + (e >> 2)) + (e & 3);                           // first_pos == own stream position
+      cnt += fl[e];
+      kk[e] = ((unsigned long long)(unsigned)ent[e].y << 32) | (unsigned)ent[e].x;
+    }
+  }
 
   // block exclusive scan of cnt
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -359,15 +365,15 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, const int *__re
   int idx = s_prefix + local;
 #pragma unroll
   for (int e = 0; e < 8; ++e)
-    if (fl[e]) { tval[sl[e]] = idx; vkeys[idx] = kk[e]; ++idx; }
+    if (fl[e]) { table[sl[e]].index = idx; vkeys[idx] = kk[e]; ++idx; }
 }
 
-__device__ __forceinline__ int table_find(const unsigned long long *__restrict__ tkeys,
-                                          const int *__restrict__ tval, unsigned mask, unsigned long long key) {
+__device__ __forceinline__ int table_find(const Entry *__restrict__ table, unsigned mask, unsigned long long key) {
   unsigned h = hash_key(key) & mask;
   for (unsigned probes = 0; probes <= mask; ++probes) {
-    unsigned long long cur = tkeys[h];
-    if (cur == key) return tval[h];
+    const int4 e = *reinterpret_cast<const int4 *>(table + h);         // key + index in one 16-byte load
+    const unsigned long long cur = ((unsigned long long)(unsigned)e.y << 32) | (unsigned)e.x;
+    if (cur == key) return e.w;
     if (cur == kEmpty) return -1;
     h = (h + 1) & mask;
   }
@@ -381,8 +387,7 @@ __device__ __forceinline__ long long floor_mod64(long long a, long long b) {
 
 __global__ void __launch_bounds__(256)
 k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
-           const int *__restrict__ tval, const unsigned long long *__restrict__ tkeys,
-           const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
+           const Entry *__restrict__ table, const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
            int64_t off_ld, const int32_t *__restrict__ foffs, int F, int64_t *__restrict__ nbr,
            int32_t *__restrict__ nbr32, int64_t nbr_ld, float *__restrict__ next_pts, int64_t next_ld,
            float next_divisor) {
@@ -396,7 +401,7 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
   if (loff || loff32) {
     for (int i = tid; i < n; i += stride) {
       const int4 s = slots[i];
-      const int v0 = tval[s.x], v1 = tval[s.y], v2 = tval[s.z], v3 = tval[s.w];
+      const int v0 = table[s.x].index, v1 = table[s.y].index, v2 = table[s.z].index, v3 = table[s.w].index;
       if (loff) {
         loff[i] = v0; loff[off_ld + i] = v1; loff[2 * off_ld + i] = v2; loff[3 * off_ld + i] = v3;
       }
@@ -414,46 +419,78 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
                          {0.0f, EFGH_E_B2, EFGH_E_C},
                          {0.0f, 0.0f, EFGH_E_C3}};
 
-  // One (filter tap, vertex) pair per thread, vertex fastest: a thread does ONE dependent table probe instead of
-  // F of them in sequence (the probes are L2-latency bound), and stores to nbr[f, :] stay coalesced.
+  // Four threads per vertex, each owning taps g, g+4, g+8, ...: a thread keeps four independent table probes in
+  // flight (the probes are L2-latency bound) and stores to nbr[f, :] stay coalesced along the vertex index.
   const bool want_nbr = F > 0 && (nbr || nbr32);
-  const int taps = want_nbr ? F : 1;
-  const long long total = (long long)taps * H;
+  const int groups = want_nbr ? 4 : 1;
+  const long long total = (long long)groups * H;
+  const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
+                  s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
   for (long long item = tid; item < total; item += stride) {
-    const int f = (int)(item / H);
-    const int h = (int)(item - (long long)f * H);
+    const int g = (int)(item / H);
+    const int h = (int)(item - (long long)g * H);
     int k[4];
     unpack_key(vkeys[h], k[0], k[1], k[2]);
     k[3] = -(k[0] + k[1] + k[2]);
     if (want_nbr) {
-      const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
-      int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
-      bool in_box = true;
+      for (int f0 = g; f0 < F; f0 += 16) {
+        unsigned long long want[4];
+        unsigned hh[4];
+        int res[4];
+        bool live[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) in_box = in_box && q[c] >= kmin[c] && q[c] <= kmax[c];
-      int res;
-      if (in_box) {
-        res = (q[0] + q[1] + q[2] + q[3] == 0) ? table_find(tkeys, tval, mask, pack_key(q[0], q[1], q[2])) : -1;
-      } else {
-        // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
-        // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
-        const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
-                        s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
-        long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
-                      (q[3] - kmin[3]);
-        res = -1;
-        if (P >= 0 && P < s0 * s1 * s2 * s3) {
-          const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
-          const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
-          const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
-          const int r0 = (int)P + kmin[0], r1 = (int)a1 + kmin[1], r2 = (int)a2 + kmin[2], r3 = (int)a3 + kmin[3];
-          if (r0 + r1 + r2 + r3 == 0) res = table_find(tkeys, tval, mask, pack_key(r0, r1, r2));
+        for (int t = 0; t < 4; ++t) {
+          const int f = f0 + 4 * t;
+          live[t] = false; res[t] = -1; want[t] = 0; hh[t] = 0;
+          if (f >= F) continue;
+          const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
+          int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
+          bool in_box = true;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) in_box = in_box && q[c] >= kmin[c] && q[c] <= kmax[c];
+          if (!in_box) {
+            // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
+            // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
+            long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
+                          (q[3] - kmin[3]);
+            if (!(P >= 0 && P < s0 * s1 * s2 * s3)) continue;
+            const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
+            const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
+            const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
+            q[0] = (int)P + kmin[0]; q[1] = (int)a1 + kmin[1]; q[2] = (int)a2 + kmin[2]; q[3] = (int)a3 + kmin[3];
+          }
+          if (q[0] + q[1] + q[2] + q[3] != 0) continue;        // not a lattice point: cannot be in the table
+          want[t] = pack_key(q[0], q[1], q[2]);
+          hh[t] = hash_key(want[t]) & mask;
+          live[t] = true;
+        }
+        int4 e[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) e[t] = live[t] ? *reinterpret_cast<const int4 *>(table + hh[t]) : make_int4(-1, -1, 0, -1);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (!live[t]) continue;
+          unsigned long long cur = ((unsigned long long)(unsigned)e[t].y << 32) | (unsigned)e[t].x;
+          int idx = e[t].w;
+          unsigned hcur = hh[t];
+          for (unsigned probes = 0; cur != want[t] && cur != kEmpty && probes <= mask; ++probes) {   // collisions: rare
+            hcur = (hcur + 1) & mask;
+            const int4 e2 = *reinterpret_cast<const int4 *>(table + hcur);
+            cur = ((unsigned long long)(unsigned)e2.y << 32) | (unsigned)e2.x;
+            idx = e2.w;
+          }
+          res[t] = cur == want[t] ? idx : -1;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int f = f0 + 4 * t;
+          if (f >= F) continue;
+          if (nbr) nbr[f * nbr_ld + h] = res[t];
+          if (nbr32) nbr32[f * nbr_ld + h] = res[t];
         }
       }
-      if (nbr) nbr[f * nbr_ld + h] = res;
-      if (nbr32) nbr32[f * nbr_ld + h] = res;
     }
-    if (next_pts && f == 0) {                                // generate_data.py:177-178
+    if (next_pts && g == 0) {                                // generate_data.py:177-178
       float q[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) q[c] = __fdiv_rn((float)k[c], next_divisor);
@@ -491,14 +528,13 @@ extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, 
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n_tiles_cap = (int)((n + kTile - 1) / kTile) + 1;
-  k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.tkeys, w.tmin, w.tiles,
-                                                         n_tiles_cap);
+  k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.table, w.tiles, n_tiles_cap);
   EFGH_LAUNCH_CHECK();
   if (n == 0) return EFGH_OK;
   k_points<<<grid_for(n, kPointThreads, 8), kPointThreads, 0, s>>>(pts, pts_ld, scale, barycentric, el_minus_gr,
-                                                                   out_ld, state, w.tkeys, w.tmin, w.slots);
+                                                                   out_ld, state, w.table, w.slots);
   EFGH_LAUNCH_CHECK();
-  k_assign<<<(int)((n + kTile - 1) / kTile), kAssignThreads, 0, s>>>(state, w.slots, w.tmin, w.tval, w.tkeys, w.vkeys, w.tiles,
+  k_assign<<<(int)((n + kTile - 1) / kTile), kAssignThreads, 0, s>>>(state, w.slots, w.table, w.vkeys, w.tiles,
                                                             (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30)));
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
@@ -522,9 +558,9 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
   }
   if (n == 0) return EFGH_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t vitems = h * (F > 0 ? F : 1);
+  const int64_t vitems = h * (F > 0 ? 4 : 1);
   const int64_t items = n > vitems ? n : vitems;
-  k_vertices<<<grid_for(items, 256, 8), 256, 0, s>>>(state, (int)n, (int)h, w.slots, w.tval, w.tkeys, w.vkeys,
+  k_vertices<<<grid_for(items, 256, 8), 256, 0, s>>>(state, (int)n, (int)h, w.slots, w.table, w.vkeys,
                                                      lattice_offset, lattice_offset32, off_ld, filter_offsets, F,
                                                      blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
                                                      next_divisor);

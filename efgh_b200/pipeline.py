@@ -102,7 +102,7 @@ class ScanPipeline(object):
             self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
-        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 1 + 2) + sum(1 for lv in self.levels if lv.get("split0"))
+        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 1 + 2)
 
     # ------------------------------------------------------------------------------------------
     def enqueue(self, pc, feat0, stream=None, timers=None):
@@ -140,8 +140,9 @@ class ScanPipeline(object):
                 _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
                 st, ws, wsn, s), "efgh_lattice_vertices"))
             S = lv["S"].data_ptr()
-            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), h_cap + 1, h_dev, 1, s),
-                                              "efgh_bcl_zero"))
+            zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
+            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), lv["Y"].data_ptr() if zero_y else None,
+                                                              lv["cmid"], lv["cmid"], h_cap, h_dev, 1, s), "efgh_bcl_zero"))
 
             def splat():
                 # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat
@@ -158,8 +159,6 @@ class ScanPipeline(object):
                 split = lv["split0"]
 
                 def conv1():
-                    if split:
-                        ck(L.efgh_bcl_zero(lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], None, h_cap, h_dev, 0, s), "efgh_bcl_zero")
                     ck(L.efgh_bcl_conv_tc(S, cin, cin, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"], h_cap, h_dev,
                                           lv["img0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
                                           lv["cmid"], self.nsplit, 1 if split else 0, s), "efgh_bcl_conv_tc")

@@ -112,11 +112,13 @@ int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_o
  * layout work.  idx_bits is 64 (reference int64 tensors) or 32.
  * ---------------------------------------------------------------------------------------------- */
 
-/* Zero-fill the first `rows` rows of S (rows x C, leading dimension ldS) and of wsum (may be NULL),
- * where rows = rows_dev ? min(*rows_dev + rows_extra, rows_cap) : rows_cap.  Lets a capacity-sized
- * splat matrix be cleared in proportion to the vertices a scan actually produced. */
-int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, int64_t rows_cap, const int32_t *rows_dev,
-                  int rows_extra, void *stream);
+/* One launch zero-fills what a BCL forward accumulates into.  With R = rows_dev ? min(*rows_dev, rows) : rows:
+ *   S (R + rows_extra rows x C, leading dimension ldS) and wsum (R + rows_extra floats) - the splat targets,
+ *   Y2 (R rows x C2, leading dimension ldY2) - the split-K accumulator of efgh_bcl_conv_tc.
+ * Any of the three may be NULL.  Cost is proportional to the vertices a scan actually produced, not to the
+ * capacity of the buffers. */
+int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, float *Y2, int64_t ldY2, int C2, int64_t rows,
+                  const int32_t *rows_dev, int rows_extra, void *stream);
 
 /* Splat (bilateralNN.py:176-191) and its density normaliser (:193-211); also the adjoint of slice.
  *   S[(off[r,n]+row_shift), c] += w[r,n] * X[c,n];  wsum[(off[r,n]+row_shift)] += w[r,n] (if wsum)

@@ -38,7 +38,7 @@ def run(H, C, F, M, label, flags=0, show=0):
     for tt, nm, ev in evs[:show]:
         print("%8.2f us  %-4s %d" % (tt / 1000.0, nm, ev))
     print("last event at %.2f us, %d events" % (evs[-1][0] / 1000.0, len(evs)))
-run(100654, 36, 15, 32, "L0 conv1 default", show=0)
+run(100654, 36, 15, 32, "L0 conv1 default", show=150)
 run(100654, 36, 15, 32, "L0 conv1 no-ldgsts", flags=1)
 run(62551, 36, 15, 64, "L1 conv1")
 run(23050, 68, 15, 128, "L2 conv1")

@@ -206,3 +206,139 @@ def test_scan_pipeline_vs_oracle(sensor, factor, dev):
         assert e1 < PER_LAYER_TOL, "pipeline BCL level %d same-input rel err %g" % (li, e1)
         assert e2 < CHAINED_TOL, "pipeline BCL level %d chained rel err %g" % (li, e2)
         gpu_prev = got_l.double()
+
+
+# ------------------------------------------------------------------------------------------------
+# wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sensor", ["nusc-32", "os1-64-64k", "hdl-64"])
+def test_lattice_scale_sweep_config5(sensor, dev):
+    """Config 5: number of scales 1..5 (prefixes of the scale map) on the three sensor densities."""
+    from oracle import lattice as ol
+    pc = synth.synth_scan(9, sensor)
+    for nscales in range(1, 6):
+        smap = synth.SCALE_MAP[:nscales]
+        want = ol.generate(pc, smap)
+        got = _run(pc, smap, dev, exact=False)
+        assert len(got) == nscales
+        for li, (g, w) in enumerate(zip(got, want)):
+            H.assert_level_equal(g, w, "%s scales=%d L%d" % (sensor, nscales, li))
+
+
+def test_lattice_deterministic_and_stream_safe(dev):
+    """Same cloud twice, and two clouds interleaved on two streams: identical results (no hidden global state)."""
+    from efgh_b200.generate_data import GenerateData
+    pcs = [torch.from_numpy(synth.synth_scan(s, "os1-64-16k")).to(dev) for s in (21, 22)]
+    gds = [GenerateData(3, synth.SCALE_MAP, "cuda", exact=False) for _ in range(2)]
+    base = [_to_np(gds[i](pcs[i])[1]) for i in range(2)]
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    outs = [None, None]
+    for rep in range(3):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = gds[i](pcs[i])[1]
+    torch.cuda.synchronize(dev)
+    for i in range(2):
+        for li, (g, w) in enumerate(zip(_to_np(outs[i]), base[i])):
+            H.assert_level_equal(g, w, "stream %d L%d" % (i, li))
+
+
+def _enet_level(dev, n_points=16384, cin=36, nout=(32, 32), do_slice=False, seed=5, radius=1, scale=1.0):
+    from efgh_b200.generate_data import GenerateData
+    from efgh_b200.bilateralNN import BilateralConvFlex
+    pc = synth.synth_scan(seed, "os1-64-16k")[:, :n_points]
+    gd = GenerateData(3, [[scale, radius]], "cuda", exact=True)
+    _, data = gd(torch.from_numpy(pc).to(dev))
+    d = data[0]
+    torch.manual_seed(seed)
+    m = BilateralConvFlex(3, radius, cin, list(nout), "cuda", True, True, True, True, do_slice, do_slice, chunk_size=-1).to(dev)
+    for p in m.parameters():
+        torch.nn.init.normal_(p, 0, 0.1)
+    feat = torch.randn(1, cin, pc.shape[1], device=dev)
+    return m, d, feat
+
+
+def _oracle_out(m, d, feat, do_slice, dtype=torch.float64, requires_grad=False):
+    from oracle import bcl as obcl
+    convs = [(c.weight.detach().cpu().clone().requires_grad_(requires_grad), c.bias.detach().cpu().clone().requires_grad_(requires_grad))
+             for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    f = feat.detach().cpu().double().requires_grad_(requires_grad)
+    sb = m.bias.detach().cpu().clone().requires_grad_(requires_grad) if do_slice else None
+    out = obcl.bcl_forward(f, d["pc1_barycentric"].cpu(), d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs,
+                           do_slice=do_slice, out_bary=d["pc1_barycentric"].cpu() if do_slice else None,
+                           out_off=d["pc1_lattice_offset"].cpu() if do_slice else None, slice_bias=sb,
+                           last_relu=m.last_relu, use_leaky=m.use_leaky, dtype=dtype)
+    return out, f, convs, sb
+
+
+@pytest.mark.parametrize("do_slice", [False, True])
+def test_bcl_enet_shape_forward_backward_vs_oracle(do_slice, dev):
+    """E-Net level-0 shape (36 -> [32,32]) on a 16k cloud, forward AND backward (autograd of the float64 oracle),
+    with and without the slice stage (reference bilateralNN.py:251-261).  Gradient tolerance 2e-5."""
+    m, d, feat = _enet_level(dev, do_slice=do_slice)
+    feat.requires_grad_(True)
+    args = (d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"],
+            d["pc1_barycentric"] if do_slice else None, d["pc1_lattice_offset"] if do_slice else None)
+    out = m(feat, *args)
+    ref, f_ref, convs, sb = _oracle_out(m, d, feat, do_slice, requires_grad=True)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert H.rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < PER_LAYER_TOL
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    out.backward(gout.to(dev))
+    ref.backward(gout.double())
+    assert H.rel_err(feat.grad.cpu().numpy(), f_ref.grad.numpy()) < 2e-5
+    mods = [c for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    for c, (W, b) in zip(mods, convs):
+        assert H.rel_err(c.weight.grad.cpu().numpy(), W.grad.numpy()) < 2e-5
+        assert H.rel_err(c.bias.grad.cpu().numpy(), b.grad.numpy()) < 2e-5
+    if do_slice:
+        assert H.rel_err(m.bias.grad.cpu().numpy(), sb.grad.numpy()) < 2e-5
+
+
+def test_bcl_radius2_filter65(dev):
+    """neighborhood_size 2 -> 65 filter taps (reference get_filter_size), tensor-core path, vs the float64 oracle."""
+    m, d, feat = _enet_level(dev, n_points=3000, cin=32, nout=(32, 64), radius=2, scale=0.5)
+    assert d["pc1_blur_neighbors"].shape[1] == 65
+    with torch.no_grad():
+        out = m(feat, d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+    ref, _, _, _ = _oracle_out(m, d, feat, False)
+    assert H.rel_err(out.cpu().numpy(), ref.numpy()) < PER_LAYER_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-5), ("fp32", 1e-5), ("tf32", 5e-3)])
+def test_bcl_precision_modes(precision, tol, dev, monkeypatch):
+    """Stated tolerances of the three arithmetic modes of the lattice convolution."""
+    from efgh_b200 import bilateralNN
+    monkeypatch.setattr(bilateralNN, "CONV_PRECISION", precision)
+    m, d, feat = _enet_level(dev, n_points=8192, cin=68, nout=(128, 128))
+    with torch.no_grad():
+        out = m(feat, d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+    ref, _, _, _ = _oracle_out(m, d, feat, False)
+    err = H.rel_err(out.cpu().numpy(), ref.numpy())
+    print("%s rel err %.2e" % (precision, err))
+    assert err < tol
+
+
+def test_bcl_partition_of_unity_fullsize(dev):
+    """Size-independent property at the full 131k size: splatting a constant 1 with density normalisation, an
+    identity filter (centre tap only) and slicing it back returns 1 at every point (barycentric weights sum to 1,
+    the normalised splat of a constant is the constant)."""
+    from efgh_b200.generate_data import GenerateData
+    from efgh_b200.bilateralNN import BilateralConvFlex
+    pc = synth.synth_scan(6, "os1-64")
+    gd = GenerateData(3, [[1.0, 1]], "cuda", exact=False)
+    _, data = gd(torch.from_numpy(pc).to(dev))
+    d = data[0]
+    C = 32
+    m = BilateralConvFlex(3, 1, C, [C, C], "cuda", False, True, True, True, True, False, chunk_size=-1).to(dev)
+    with torch.no_grad():
+        m.blur_conv[0].weight.zero_(); m.blur_conv[0].bias.zero_()
+        m.blur_conv[2].weight.zero_(); m.blur_conv[2].bias.zero_()
+        for c in range(C):
+            m.blur_conv[0].weight[c, c, 0, 0] = 1.0      # tap 0 is the vertex itself
+            m.blur_conv[2].weight[c, c, 0, 0] = 1.0
+        feat = torch.ones(1, C, pc.shape[1], device=dev)
+        out = m(feat, d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"],
+                d["pc1_barycentric"], d["pc1_lattice_offset"])
+    assert tuple(out.shape) == (1, C, pc.shape[1])
+    assert float((out - 1).abs().max()) < 2e-4       # 1e-5 in the normaliser's denominator, fp32 sums

@@ -17,4 +17,10 @@ def __getattr__(name):
     if name == "BilateralConvFlex":
         from .bilateralNN import BilateralConvFlex
         return BilateralConvFlex
+    if name == "Enet":
+        from .enet import Enet
+        return Enet
+    if name == "ScanPipeline":
+        from .pipeline import ScanPipeline
+        return ScanPipeline
     raise AttributeError(name)

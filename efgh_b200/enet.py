@@ -1,0 +1,145 @@
+"""E-Net on the B200 lattice path - the consumer of GenerateData / BilateralConvFlex.
+
+Mirrors reference nets/enet.py:12-197 (same sub-module names, so reference checkpoints load): a 3-layer
+pointwise stem, the five splat-only bilateral convolution layers fed `cat(el_minus_gr, previous output)`,
+a Conv1d/BN head, global max-pool, MLP, gravity-normal and the rotation that aligns it with +z.
+
+Only the lattice build and the BCLs run on this repo's CUDA kernels; the stem / head are stock PyTorch
+(cuDNN / cuBLAS) - they are row (f)1 "next" of the scope table, not part of the measured path.
+The two geometry helpers of reference common/torch_utils.py:126-146,170-200 are restated without their
+per-sample Python loops and `.tolist()` host syncs.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .bilateralNN import BilateralConvFlex
+from .generate_data import GenerateData
+
+LEAKY_RATE = 0.1
+
+
+def conv_1x1(in_channels, out_channels, use_leaky=False):
+    """reference nets/net_utils.py:35-43 (Conv1d k=1 + ReLU / LeakyReLU(0.1), N(0,1e-3) init handled by caller)."""
+    act = nn.ReLU(inplace=True) if not use_leaky else nn.LeakyReLU(LEAKY_RATE, inplace=True)
+    return nn.Sequential(nn.Conv1d(in_channels, out_channels, 1, 1, 0, bias=True), act)
+
+
+def normal_vector_3d_from_abs_sign(abs_, sign):
+    """reference common/torch_utils.py:126-146: abs (B,3,1), sign logits (B,8) -> (B,3,1).
+    argmax of the 8-way sign code; bit 2 -> x, bit 1 -> y, bit 0 -> z; 0 means negative."""
+    code = torch.argmax(sign, dim=1)                                  # softmax is monotone: same argmax
+    bits = torch.stack(((code >> 2) & 1, (code >> 1) & 1, code & 1), dim=1)
+    sgn = torch.where(bits == 0, -torch.ones_like(bits), bits).to(abs_.dtype)
+    return abs_ * sgn[:, :, None]
+
+
+def rotation_matrix_between_two_vectors(srce, dest):
+    """reference common/torch_utils.py:170-200: (B,3,1) x (B,3,1) -> (B,4,4) rotation taking srce onto dest
+    (Rodrigues form I + K + K^2 (1-c)/s^2, with the reference's special cases for c = +-1)."""
+    a, b = srce[:, :, 0], dest[:, :, 0].to(srce.device).expand_as(srce[:, :, 0])
+    v = torch.cross(a, b, dim=1)
+    c = (a * b).sum(1)
+    s2 = (v * v).sum(1)
+    zero = torch.zeros_like(c)
+    K = torch.stack((torch.stack((zero, -v[:, 2], v[:, 1]), 1),
+                     torch.stack((v[:, 2], zero, -v[:, 0]), 1),
+                     torch.stack((-v[:, 1], v[:, 0], zero), 1)), 1)   # (B,3,3)
+    K = K.detach()                                                     # the reference builds kmat with torch.tensor(...): no grad
+    eye3 = torch.eye(3, device=a.device, dtype=a.dtype)[None]
+    safe = torch.where(s2 > 0, s2, torch.ones_like(s2))
+    rot3 = eye3 + K + torch.bmm(K, K) * ((1 - c) / safe)[:, None, None]
+    out = torch.eye(4, device=a.device, dtype=a.dtype)[None].repeat(a.shape[0], 1, 1)
+    out[:, :3, :3] = rot3
+    same = (1 - c) == 0
+    opp = (1 + c) == 0
+    if bool(same.any()) or bool(opp.any()):
+        eye4 = torch.eye(4, device=a.device, dtype=a.dtype)
+        for i in torch.nonzero(same | opp).flatten().tolist():
+            if bool(same[i]):
+                out[i] = eye4
+            else:
+                m = -eye4.clone()
+                if float(a[i, 0]) == 0.0 and float(b[i, 0]) == 0.0:
+                    m[0, 0] = 1
+                elif float(a[i, 2]) == 0.0 and float(b[i, 2]) == 0.0:
+                    m[2, 2] = 1
+                out[i] = m
+    return out
+
+
+class Enet(nn.Module):
+    def __init__(self, args):
+        """args: the reference's config dict (keys dim, scale_map, DEVICE, use_leaky, bcn_use_bias, bcn_use_norm,
+        last_relu - reference configs/train_rellis.yaml:8-35)."""
+        super(Enet, self).__init__()
+        dim = args['dim']
+        scales_filter_map = args['scale_map']
+        chunk_size = -1
+        self.device = args['DEVICE']
+        self.generate_data = GenerateData(dim, scales_filter_map, self.device, exact=args.get('exact_lattice', False))
+
+        self.conv_in = nn.Sequential(
+            conv_1x1(dim, 32, use_leaky=args['use_leaky']),
+            conv_1x1(32, 32, use_leaky=args['use_leaky']),
+            conv_1x1(32, 32, use_leaky=args['use_leaky']),
+        )
+        # (Conv1d keeps PyTorch's default init: the reference's init_weights only touches Conv2d / Linear, net_utils.py:16-33)
+
+        def bcn(level, cin, couts):
+            return BilateralConvFlex(dim, scales_filter_map[level][1], cin, couts, self.device,
+                                     use_bias=args['bcn_use_bias'], use_leaky=args['use_leaky'],
+                                     use_norm=args['bcn_use_norm'], do_splat=True, do_slice=False,
+                                     last_relu=args['last_relu'], chunk_size=chunk_size)
+
+        self.bcn1 = bcn(0, 32 + dim + 1, [32, 32])
+        self.bcn2 = bcn(1, 32 + dim + 1, [64, 64])
+        self.bcn3 = bcn(2, 64 + dim + 1, [128, 128])
+        self.bcn4 = bcn(3, 128 + dim + 1, [256, 256])
+        self.bcn5 = bcn(4, 256 + dim + 1, [256, 256])
+
+        self.conv_gn_1 = nn.Conv1d(256, 128, 1)
+        self.conv_gn_2 = nn.Conv1d(128, 128, 1)
+        self.conv_gn_3 = nn.Conv1d(128, 128, 1)
+        self.bn_gn_1 = nn.BatchNorm1d(128)
+        self.bn_gn_2 = nn.BatchNorm1d(128)
+        self.bn_gn_3 = nn.BatchNorm1d(128)
+        self.lin_gn_1 = nn.Linear(128, 128)
+        self.lin_gn_2 = nn.Linear(128, 128)
+        self.lin_gn_3 = nn.Linear(128, 32)
+        self.lin_gn_abs = nn.Linear(32, 3)
+        self.lin_gn_sgn = nn.Linear(32, 8)
+        self.softmax = nn.Softmax(dim=1)
+        self.target_e3_vector = torch.unsqueeze(torch.unsqueeze(torch.tensor([0., 0., 1.]), 0), -1)
+
+    def forward(self, pc, check=False):
+        """pc (1, 3, N) on the GPU.  Returns the reference's dict (enet.py:179-187)."""
+        pc1, generated_data = self.generate_data(pc[0, :, :])         # enet.py:107 (batch entry 0 only, like the reference)
+        pc1 = torch.unsqueeze(pc1, 0)
+        out = self.conv_in(pc1[:, :3, :])
+        bcn_outs = []
+        for level, layer in enumerate((self.bcn1, self.bcn2, self.bcn3, self.bcn4, self.bcn5)):
+            d = generated_data[level]
+            out = layer(torch.cat((d['pc1_el_minus_gr'], out), dim=1),
+                        in_barycentric=d['pc1_barycentric'], in_lattice_offset=d['pc1_lattice_offset'],
+                        blur_neighbors=d['pc1_blur_neighbors'], out_barycentric=None, out_lattice_offset=None)
+            bcn_outs.append(out)
+        if check:
+            for i, o in enumerate(bcn_outs):
+                print("[E] pc1_out%d          " % (i + 1), o.size())
+
+        gn = F.relu(self.bn_gn_1(self.conv_gn_1(out)))
+        gn = F.relu(self.bn_gn_2(self.conv_gn_2(gn)))
+        gn = F.relu(self.bn_gn_3(self.conv_gn_3(gn)))
+        fc = torch.max(gn, 2, keepdim=True)[0]
+        fc = fc.view(fc.size(0), -1)
+        fc = F.relu(self.lin_gn_1(fc))
+        fc = F.relu(self.lin_gn_2(fc))
+        fc = F.relu(self.lin_gn_3(fc))
+        gn_sgn = self.lin_gn_sgn(fc)
+        gn_abs_0 = self.softmax(self.lin_gn_abs(fc))
+        gn_abs = torch.unsqueeze(gn_abs_0 / torch.sqrt(torch.sum(torch.pow(gn_abs_0, 2), 1, keepdim=True)), -1)
+        e_gn = normal_vector_3d_from_abs_sign(gn_abs, gn_sgn)
+        e_T = rotation_matrix_between_two_vectors(e_gn, self.target_e3_vector)
+        return {'e_gn_abs': gn_abs, 'e_gn_sgn': gn_sgn, 'e_gn': e_gn, 'e_l': e_T, 'sensor2_T_sensor1': e_T,
+                'network': 'E', 'bcn_outputs': bcn_outs}

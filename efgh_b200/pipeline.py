@@ -46,6 +46,8 @@ class ScanPipeline(object):
         self.precision = precision
         self.nsplit = {"3xtf32": 3, "tf32": 1, "fp32": 0}[precision]
         self._graphs = {}
+        self.overlap_lattice = True
+        self._lat_stream = None
         self.gd = GenerateData(3, scales_filter_map, "cuda")
         dev = self.dev
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
@@ -109,11 +111,25 @@ class ScanPipeline(object):
         """pc (3,N) f32, feat0 (C_stem,N) f32 device tensors.  Enqueues the whole scan on `stream` (default:
         current).  Returns the last level's output buffer Z (h_cap, C_out) - valid rows = states[-1, 1].
         timers: optional dict; stages whose name is a key (or every stage if "*" is a key) get a CUDA event
-        pair appended to timers[name]."""
+        pair appended to timers[name].
+
+        The lattice build of level l+1 depends only on level l's vertices, not on level l's BCL, so (unless stages
+        are being timed) the five lattice levels run on a private side stream and the BCL chain follows them on
+        `stream` through one event per level: the ~0.2 ms lattice chain hides behind the BCL chain."""
         L, ck = self.L, _capi.check
-        s = (stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.dev).cuda_stream)
+        main = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        s = main.cuda_stream
         assert pc.shape[-1] == self.n0 and pc.stride(-1) == 1 and feat0.stride(-1) == 1
         ws, wsn = self.ws.data_ptr(), self.ws.numel()
+        lat = None
+        if self.overlap_lattice and timers is None:
+            if self._lat_stream is None:
+                self._lat_stream = torch.cuda.Stream(self.dev)
+            lat = self._lat_stream
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            lat.wait_event(ev0)                       # inputs ready / previous scan of this pipeline finished
+        s_lat = lat.cuda_stream if lat is not None else s
 
         def timed(name, fn):
             if timers is None or not (name in timers or "*" in timers):
@@ -134,11 +150,15 @@ class ScanPipeline(object):
             h_dev = st + 4           # &state.hash_cnt
             timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points(
                 pts_ptr, pts_ld, n_cap, n_dev, lv["scale"], lv["bary"].data_ptr(), lv["elmgr"].data_ptr(), n_cap, h_cap,
-                st, ws, wsn, s), "efgh_lattice_points"))
+                st, ws, wsn, s_lat), "efgh_lattice_points"))
             timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices(
                 n_cap, _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap, lv["offs"].data_ptr(), lv["F"], h_cap,
                 _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
-                st, ws, wsn, s), "efgh_lattice_vertices"))
+                st, ws, wsn, s_lat), "efgh_lattice_vertices"))
+            if lat is not None:
+                ev = torch.cuda.Event()
+                ev.record(lat)
+                main.wait_event(ev)                   # BCL of this level may start; the next level's lattice runs on
             S = lv["S"].data_ptr()
             zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
             timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), lv["Y"].data_ptr() if zero_y else None,

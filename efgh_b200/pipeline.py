@@ -155,14 +155,15 @@ class ScanPipeline(object):
                 n_cap, _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap, lv["offs"].data_ptr(), lv["F"], h_cap,
                 _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
                 st, ws, wsn, s_lat), "efgh_lattice_vertices"))
+            S = lv["S"].data_ptr()
+            zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
+            # zero-fill of this level's accumulators: on the lattice stream, i.e. off the BCL chain's critical path
+            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), lv["Y"].data_ptr() if zero_y else None,
+                                                              lv["cmid"], lv["cmid"], h_cap, h_dev, 1, s_lat), "efgh_bcl_zero"))
             if lat is not None:
                 ev = torch.cuda.Event()
                 ev.record(lat)
                 main.wait_event(ev)                   # BCL of this level may start; the next level's lattice runs on
-            S = lv["S"].data_ptr()
-            zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
-            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), lv["Y"].data_ptr() if zero_y else None,
-                                                              lv["cmid"], lv["cmid"], h_cap, h_dev, 1, s), "efgh_bcl_zero"))
 
             def splat():
                 # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat

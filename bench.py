@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="concurrent scan pipelines per GPU")
+    ap.add_argument("--scan-batch", type=int, default=4,
+                    help="scans per launch sequence (ragged batched lattices, SURVEY §8 f2); 1 = one launch sequence per scan")
     ap.add_argument("--sensor", default=SENSOR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage timing table to stderr")
@@ -183,7 +185,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, P = args.batch, max(1, min(args.streams, args.batch))
+    B = args.batch
+    G = max(1, min(args.scan_batch, B))                 # scans per launch sequence
+    if B % G:
+        raise SystemExit("bench.py: --batch must be a multiple of --scan-batch")
+    NG = B // G                                         # launch sequences ("groups") per step
+    P = max(1, min(args.streams, NG))
     weights = make_enet_weights(synth.ENET_BCL)
     # this rank's scans: global scan index = rank + world * j  (scan-index sharding)
     seeds = [rank + world * j for j in range(B)]
@@ -191,19 +198,21 @@ def run_ours(args):
     N = clouds[0].shape[1]
     rng = np.random.default_rng(1000 + rank)
     feats = [rng.standard_normal((32, N)).astype(np.float32) for _ in range(B)]
-    pc_dev = [torch.from_numpy(c).to(dev) for c in clouds]
-    ft_dev = [torch.from_numpy(f).to(dev) for f in feats]
-    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0) for _ in range(P)]
+    # resident inputs, one (3, G*N) / (32, G*N) pair per group: scan b of the group in columns [b*N, (b+1)*N)
+    pc_dev = [torch.from_numpy(np.concatenate(clouds[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
+    ft_dev = [torch.from_numpy(np.concatenate(feats[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
+    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G) for _ in range(P)]
+    pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
     main = torch.cuda.current_stream(dev)
 
     use_graph = not args.no_graph
     graphs = None
-    if use_graph:   # one CUDA graph per resident scan (captures the whole 5-level scan on that scan's stream)
-        graphs = [pipes[j % P].graph_for(pc_dev[j], ft_dev[j], streams[j % P]) for j in range(B)]
+    if use_graph:   # one CUDA graph per resident group (captures the whole 5-level launch sequence on that group's stream)
+        graphs = [pipes[j % P].graph_for(pc_dev[j], ft_dev[j], streams[j % P]) for j in range(NG)]
 
     def step(timers=None):
-        for j in range(B):
+        for j in range(NG):
             if use_graph and timers is None:
                 with torch.cuda.stream(streams[j % P]):
                     graphs[j].replay()
@@ -241,9 +250,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
-    counts = pipes[0].counts()
+    counts = pipes[0].counts()                          # totals over the G scans of a group
     for p in pipes[1:]:
         p.counts()
+    vs = pipes[0].vertex_starts()
+    counts_scan0 = [v[1] - v[0] for v in vs]
 
     # ---- timed region, inputs resident in HBM; the dominant kernel carries CUDA events on its own stream
     DOM = "L0.conv1"
@@ -263,12 +274,17 @@ def run_ours(args):
     out_rows = 2048
     pc_pin = [torch.from_numpy(c).pin_memory() for c in clouds]
     ft_pin = [torch.from_numpy(f).pin_memory() for f in feats]
-    out_pin = [torch.empty((out_rows, synth.ENET_BCL[-1][1][-1]), dtype=torch.float32).pin_memory() for _ in range(B)]
-    st_pin = [torch.empty((len(synth.SCALE_MAP), 24), dtype=torch.int32).pin_memory() for _ in range(B)]
+    out_pin = [torch.empty((out_rows, synth.ENET_BCL[-1][1][-1]), dtype=torch.float32).pin_memory() for _ in range(NG)]
+    st_pin = [torch.empty((len(synth.SCALE_MAP), 24), dtype=torch.int32).pin_memory() for _ in range(NG)]
+    vs_pin = [torch.empty((len(synth.SCALE_MAP), G + 1), dtype=torch.int32).pin_memory() for _ in range(NG)]
 
     def step_e2e():
-        for j in range(B):
-            pipes[j % P].forward_host(pc_pin[j], ft_pin[j], out_pin[j], st_pin[j], stream=streams[j % P], use_graph=use_graph)
+        for j in range(NG):
+            if G == 1:
+                pipes[j % P].forward_host(pc_pin[j], ft_pin[j], out_pin[j], st_pin[j], stream=streams[j % P], use_graph=use_graph)
+            else:
+                pipes[j % P].forward_host(pc_pin[j * G:(j + 1) * G], ft_pin[j * G:(j + 1) * G], out_pin[j], st_pin[j],
+                                          stream=streams[j % P], use_graph=use_graph, starts_host=vs_pin[j])
 
     for _ in range(2):
         step_e2e()
@@ -276,20 +292,22 @@ def run_ours(args):
     ms_e2e = timed_region(step_e2e, e2e_steps)
     e2e_value = B * world * e2e_steps / (ms_e2e * 1e-3)
     h2d = B * (clouds[0].nbytes + feats[0].nbytes)
-    d2h = B * (out_pin[0].numel() * 4 + st_pin[0].numel() * 4)
-    assert int(st_pin[0][0, 1]) == counts[0] or B > P  # the records really came back
+    d2h = NG * (out_pin[0].numel() * 4 + st_pin[0].numel() * 4 + (vs_pin[0].numel() * 4 if G > 1 else 0))
+    assert int(st_pin[0][0, 1]) == counts[0] or NG > P  # the records really came back
 
     # ---- single-scan latency and per-stage table (outside the timed region)
     lat = []
+    pc1_dev, ft1_dev = pc_dev[0][:, :N].contiguous(), ft_dev[0][:, :N].contiguous()
+    g1 = pipe1.graph_for(pc1_dev, ft1_dev, streams[0]) if use_graph else None
     for _ in range(5):
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(streams[0])
         if use_graph:
             with torch.cuda.stream(streams[0]):
-                graphs[0].replay()
+                g1.replay()
         else:
-            pipes[0].enqueue(pc_dev[0], ft_dev[0], stream=streams[0])
+            pipe1.enqueue(pc1_dev, ft1_dev, stream=streams[0])
         b.record(streams[0])
         torch.cuda.synchronize(dev)
         lat.append(a.elapsed_time(b))
@@ -316,15 +334,17 @@ def run_ours(args):
     dom_bytes = 4 * lv0["cin"] * (H0 + 1) + 4 * (H0 + 1) + 4 * lv0["F"] * H0 + 4 * lv0["cmid"] * H0 + 4 * K0 * lv0["cmid"]
     dom_flops = 2.0 * H0 * K0 * lv0["cmid"]
     total_bytes, _ = pipes[0].algorithmic_bytes(counts)
+    total_bytes /= G                                    # per scan
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")   # dram bytes per launch from one `ncu --set full` capture
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch") if tj.get("scans_per_launch", 1) == G else None
         except Exception:
             traffic = None
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roof = {"kernel": "k_conv_tc level 0: neighbour gather + (15,1) convolution (%s)" % pipes[0].precision, "bound": "hbm",
+    roof = {"kernel": "k_conv_tc level 0 (%d scans per launch): neighbour gather + (15,1) convolution (%s)" % (G, pipes[0].precision), "bound": "hbm",
             "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
             "peak_source": peaks["source"] + " copy bandwidth",
             "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes, "tensor_tflops": dom_flops / (dom_ms * 1e-3) / 1e12,
@@ -336,16 +356,16 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd" % (args.sensor, N),
-                   "scans_per_gpu_per_step": B, "concurrent_pipelines": P, "levels_H": counts,
+                   "scans_per_gpu_per_step": B, "scans_per_launch_sequence": G, "concurrent_pipelines": P, "levels_H": counts_scan0,
                    "l2_policy": "inputs larger than L2 (%d scans x %.1f MB resident, cycled)" % (B, (clouds[0].nbytes + feats[0].nbytes) / 1e6),
                    "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                    "algorithmic_MB_per_scan": total_bytes / 1e6,
                    "scan_roofline_frac": total_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": pipes[0].launches_per_scan * B * args.steps,
+        "gpu_launches": pipes[0].launches_per_scan * NG * args.steps,
         "roofline": roof,
-        "stages_us": stages,
+        "stages_us": stages,          # per launch sequence (G scans), eager single-stream pass
     }
     if world == 1 and not args.no_cpu_baseline:
         try:

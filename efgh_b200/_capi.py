@@ -17,9 +17,14 @@ SIGNATURES = {
     "efgh_last_error": (ctypes.c_char_p, []),
     "efgh_version": (i32, []),
     "efgh_device_sm_count": (i32, []),
+    "efgh_copy_matrix_async": (i32, [vp, i64, vp, i64, i64, i64, i32, vp]),
     "efgh_lattice_workspace_bytes": (sz, [i64]),
     "efgh_lattice_points": (i32, [vp, i64, i64, vp, f32, vp, vp, i64, i64, vp, vp, sz, vp]),
     "efgh_lattice_vertices": (i32, [i64, vp, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, f32, vp, vp, sz, vp]),
+    "efgh_lattice_batch_workspace_bytes": (sz, [i32, i64, i64]),
+    "efgh_lattice_batch_info_ints": (i64, [i32]),
+    "efgh_lattice_points_batch": (i32, [vp, i64, i64, vp, i32, i64, f32, vp, vp, i64, i64, vp, vp, vp, sz, vp]),
+    "efgh_lattice_vertices_batch": (i32, [i64, vp, i32, i64, vp, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, f32, vp, vp, vp, sz, vp]),
     "efgh_bcl_scatter": (i32, [vp, i64, i64, i32, vp, i64, i64, i32, i64, vp, vp, i64, vp, i32, i64, i32, vp, i64, vp, vp]),
     "efgh_bcl_zero": (i32, [vp, i64, i32, vp, vp, i64, i32, i64, vp, i32, vp]),
     "efgh_bcl_inv_norm": (i32, [vp, vp, i64, vp, i32, vp]),

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _capi
+from .generate_data import blur_offsets
 
 DELETE_TMP_VARIABLES = False
 
@@ -147,6 +148,92 @@ def conv_dgrad(dY, act_out, act, nbr, Wt, C, rows):
     return dX
 
 
+def _act_bwd(dY, act_out, act, out=None):
+    """dY * act'(Y) (the activation's derivative is read off its output, as the kernels' loaders do)."""
+    if act == _ACT["relu"]:
+        return torch.mul(dY, act_out > 0, out=out)
+    if act == _ACT["leaky"]:
+        return torch.where(act_out > 0, dY, 0.1 * dY, out=out)
+    if out is None:
+        return dY
+    out.copy_(dY)
+    return out
+
+
+def _tc_image(Wt, nsplit):
+    K, M = Wt.shape
+    L = _capi.lib()
+    img = torch.empty(L.efgh_bcl_packed_weight_bytes(K, M, nsplit) // 4, dtype=torch.float32, device=Wt.device)
+    _capi.check(L.efgh_bcl_pack_weights(Wt.data_ptr(), K, M, nsplit, img.data_ptr(), _capi.stream_ptr()),
+                "efgh_bcl_pack_weights")
+    return img
+
+
+def neighbours_symmetric(nbr, mirror):
+    """True when `g = nbr[f, h] >= 0` implies `nbr[mirror[f], g] == h` for every tap - the property that lets
+    the data gradient of the lattice convolution be computed as a gather over the same neighbour table.  It
+    holds whenever no neighbour key left the hash's key box (the reference's key2int aliasing,
+    nets/transforms.py:124-131, is the only way to break it).  One device reduction + one host read."""
+    nb = nbr[0]
+    H = nb.shape[1]
+    back = torch.gather(nb[list(mirror)], 1, nb.clamp(min=0).long())
+    here = torch.arange(H, device=nb.device, dtype=back.dtype)[None]
+    return bool(((back == here) | (nb < 0)).all())
+
+
+def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit):
+    """Data gradient of one convolution on the tensor-core kernel, or None when the shape does not fit it.
+
+    The scatter form dX[nbr[f,h]+1, c] += sum_m dY[h,m] W[m,c,f] becomes, through the lattice's symmetry
+    (tap f of h is g  <=>  tap mirror(f) of g is h), the forward-shaped gather
+        dX[g+1, c] = sum_t sum_m dYm[nbr[t,g]+1, m] * W[m, c, mirror(t)],
+    i.e. efgh_bcl_conv_tc over the same neighbour table with re-laid weights.  The kernel wants an output
+    width that is a multiple of 32, so the first C % 32 channels (the four el_minus_gr channels of E-Net) stay
+    on the FFMA scatter kernel."""
+    L = _capi.lib()
+    h, Mk = dY.shape
+    C = W.shape[1]
+    if nbr is None:
+        if not L.efgh_bcl_conv_tc_supported(Mk, 1, C, nsplit):
+            return None
+        dYm = _act_bwd(dY, act_out, act)
+        if not dYm.is_contiguous():
+            dYm = dYm.contiguous()
+        img = _tc_image(W[:, :, 0, 0].contiguous(), nsplit)          # (K = M_k, C)
+        split = L.efgh_bcl_conv_tc_groups(Mk) > 1
+        dX = (torch.zeros if split else torch.empty)((h, C), dtype=torch.float32, device=dY.device)
+        _capi.check(L.efgh_bcl_conv_tc(dYm.data_ptr(), Mk, Mk, None, 0, None, 64, 0, 1, h, None, img.data_ptr(), None, C,
+                                       0, dX.data_ptr(), C, nsplit, 1 if split else 0, _capi.stream_ptr()),
+                    "efgh_bcl_conv_tc(dgrad)")
+        return dX
+    rem = C % 32
+    Cg = C - rem
+    nb2, nb_ld = _rows(nbr)
+    F = nb2.shape[0]
+    if rem % 4 or Cg == 0 or not L.efgh_bcl_conv_tc_supported(Mk, F, Cg, nsplit):
+        return None
+    if not neighbours_symmetric(nbr, mirror):
+        return None
+    Xp = torch.empty((h + 1, Mk), dtype=torch.float32, device=dY.device)
+    Xp[0].zero_()                                                     # the sink row: absent neighbours
+    _act_bwd(dY, act_out, act, out=Xp[1:])
+    Wg = W[:, rem:, :, 0][:, :, list(mirror)].permute(2, 0, 1).reshape(F * Mk, Cg).contiguous()
+    img = _tc_image(Wg, nsplit)
+    dX = torch.zeros((rows, C), dtype=torch.float32, device=dY.device)
+    split = L.efgh_bcl_conv_tc_groups(F * Mk) > 1
+    out = dX[1:, rem:]
+    _capi.check(L.efgh_bcl_conv_tc(Xp.data_ptr(), Mk, Mk, None, 0, nb2.data_ptr(), _idx_bits(nb2), nb_ld, F, h, None,
+                                   img.data_ptr(), None, Cg, 0, out.data_ptr(), C, nsplit, 1 if split else 0,
+                                   _capi.stream_ptr()), "efgh_bcl_conv_tc(dgrad)")
+    if rem:
+        Wr = W[:, :rem, :, 0].permute(2, 1, 0).reshape(F * rem, Mk).contiguous()       # (F*rem, M) for the scatter form
+        _capi.check(L.efgh_bcl_conv_dgrad(dY.data_ptr(), dY.stride(0), _capi.ptr(act_out),
+                                          act_out.stride(0) if act_out is not None else 0, act, Mk, nb2.data_ptr(),
+                                          _idx_bits(nb2), nb_ld, F, h, None, Wr.data_ptr(), rem, dX.data_ptr(), C,
+                                          _capi.stream_ptr()), "efgh_bcl_conv_dgrad")
+    return dX
+
+
 def conv_wgrad(X, row_scale, nbr, dY, act_out, act, want_bias):
     h, M = dY.shape
     C = X.shape[1]
@@ -181,7 +268,7 @@ class _BCLFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, features, in_bary, in_off, nbr, out_bary, out_off, slice_bias, *wb):
-        do_splat, do_slice, use_norm, final_act = cfg
+        do_splat, do_slice, use_norm, final_act = cfg[:4]
         if features.shape[0] != 1:
             raise ValueError("BilateralConvFlex: batch size must be 1 (reference bilateralNN.py:162-165)")
         feat = features[0]
@@ -216,19 +303,21 @@ class _BCLFunction(torch.autograd.Function):
         ctx.n_in = feat.shape[-1]
         ctx.acts = acts
         ctx.has_slice_bias = slice_bias is not None
-        ctx.save_for_backward(in_bary, in_off, nbr, out_bary, out_off, inv, *xs, *ys, *wts)
+        ctx.save_for_backward(in_bary, in_off, nbr, out_bary, out_off, inv, *xs, *ys, *wts, *wb[0::2])
         ctx.nconv = nconv
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        do_splat, do_slice, use_norm, final_act = ctx.cfg
+        do_splat, do_slice, use_norm, final_act, mirror = ctx.cfg
         saved = ctx.saved_tensors
         in_bary, in_off, nbr, out_bary, out_off, inv = saved[:6]
         nconv = ctx.nconv
         xs = saved[6:6 + nconv]
         ys = saved[6 + nconv:6 + 2 * nconv]
         wts = saved[6 + 2 * nconv:6 + 3 * nconv]
+        Ws = saved[6 + 3 * nconv:6 + 4 * nconv]
+        nsplit = _NSPLIT.get(CONV_PRECISION, 0)
         H = nbr.shape[-1]
         g = gout[0]
         if g.dtype != torch.float32:
@@ -263,7 +352,12 @@ class _BCLFunction(torch.autograd.Function):
                 if first and not ctx.needs_input_grad[1]:
                     dY = None
                     break
-                dY = conv_dgrad(dY, act_out, act, nbr if first else None, wts[k], X.shape[1], X.shape[0])
+                dX = None
+                if nsplit:
+                    dX = conv_dgrad_tc(dY, act_out, act, nbr if first else None, Ws[k], mirror, X.shape[0], nsplit)
+                if dX is None:
+                    dX = conv_dgrad(dY, act_out, act, nbr if first else None, wts[k], X.shape[1], X.shape[0])
+                dY = dX
             dfeat = None
             if ctx.needs_input_grad[1] and dY is not None:
                 if do_splat:
@@ -294,6 +388,8 @@ class BilateralConvFlex(nn.Module):
         self.d1 = d + 1
         self.neighborhood_size = neighborhood_size
         self.filter_size = self.get_filter_size()
+        offs = [tuple(o) for o in blur_offsets(neighborhood_size, d).tolist()]
+        self._mirror = tuple(offs.index(tuple(-v for v in o)) for o in offs)     # tap f <-> the tap with the negated offset
         self.num_input = num_input
         self.num_output = num_output
         self.DEVICE = DEVICE
@@ -346,7 +442,7 @@ class BilateralConvFlex(nn.Module):
         final_act = 0
         if self.last_relu:
             final_act = _ACT["leaky"] if self.use_leaky else _ACT["relu"]
-        cfg = (self.do_splat, self.do_slice, self.use_norm, final_act)
+        cfg = (self.do_splat, self.do_slice, self.use_norm, final_act, self._mirror)
         wb = []
         for m in self.blur_conv:
             if isinstance(m, nn.Conv2d):

@@ -424,7 +424,9 @@ k_dgrad(const float *__restrict__ dY, int64_t ldY, const float *__restrict__ act
 }
 
 // dWt[f*C+c, m] += sum_h A[h, f*C+c] * dYm[h, m];  dbias[m] += sum_h dYm[h, m]
-// grid: x = split over vertices (chunks of HC), y = tiles of flat k, z = tiles of m
+// grid: x = split over vertices (chunks of kWgradChunk), y = (filter tap f, tile of input channels), z = tiles of m.
+// A K-tile never straddles a tap, so the neighbour row of each of the 16 vertices of a step is looked up once and
+// the gathered rows are read with coalesced 16-byte loads along the channels.
 constexpr int kWgradChunk = 1024;
 template <typename IdxT, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256)
@@ -432,40 +434,77 @@ k_wgrad(const float *__restrict__ X, int64_t ldX, int C, const float *__restrict
         const void *__restrict__ nbr, int64_t nbr_ld, int F, int h_host, const int32_t *h_dev,
         const float *__restrict__ dY, int64_t ldY, const float *__restrict__ act_out, int64_t ldA, int act,
         int M, float *dWt, float *dbias) {
-  __shared__ float As[BK][BM + 4];  // [h-chunk][flat k]
-  __shared__ float Bs[BK][BN + 4];  // [h-chunk][m]
+  __shared__ float As[BK][BM + 4];  // [vertex of the step][input channel]
+  __shared__ float Bs[BK][BN + 4];  // [vertex of the step][m]
+  __shared__ int s_row[BK];
+  __shared__ float s_scl[BK];
   const int H = h_dev ? min(*h_dev, h_host) : h_host;
-  const int K = F * C;
-  const int k0 = blockIdx.y * BM, m0 = blockIdx.z * BN;
+  const int ctiles = (C + BM - 1) / BM;
+  const int f = blockIdx.y / ctiles, c0 = (blockIdx.y - f * ctiles) * BM, m0 = blockIdx.z * BN;
+  const bool vecA = (C % 4 == 0) && (ldX % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const bool vecB = (M % 4 == 0) && (ldY % 4 == 0) && ((reinterpret_cast<uintptr_t>(dY) & 15) == 0) &&
+                    (!act_out || (ldA % 4 == 0 && (reinterpret_cast<uintptr_t>(act_out) & 15) == 0));
   Tile<BM, BN, TM, TN> T;
   for (int hc = blockIdx.x * kWgradChunk; hc < H; hc += gridDim.x * kWgradChunk) {
     T.zero();
     float bsum = 0.f;
     const int hend = min(H, hc + kWgradChunk);
     for (int h0 = hc; h0 < hend; h0 += BK) {
-      for (int u = threadIdx.x; u < BK * BM; u += 256) {
-        const int hh = u / BM, kk = u % BM;
-        const int h = h0 + hh, k = k0 + kk;
-        float v = 0.f;
-        if (h < hend && k < K) {
-          const int f = k / C, c = k - f * C;
-          const int row = nbr ? load_idx<IdxT>(nbr, f * nbr_ld + h) + 1 : h;
-          if (row > 0 || (row == 0 && !nbr)) {
-            v = __ldg(X + (int64_t)row * ldX + c);
-            if (row_scale) v *= __ldg(row_scale + row);
-          }
+      if (threadIdx.x < BK) {
+        const int h = h0 + threadIdx.x;
+        int row = -1;
+        if (h < hend) {
+          row = nbr ? load_idx<IdxT>(nbr, f * nbr_ld + h) + 1 : h;
+          if (nbr && row == 0) row = -1;                              // sink row: zeros
         }
-        As[hh][kk] = v;
+        s_row[threadIdx.x] = row;
+        s_scl[threadIdx.x] = (row >= 0 && row_scale) ? __ldg(row_scale + row) : 1.0f;
       }
-      for (int u = threadIdx.x; u < BK * BN; u += 256) {
-        const int hh = u / BN, mm = u % BN;
-        const int h = h0 + hh, m = m0 + mm;
-        float v = 0.f;
-        if (h < hend && m < M) {
-          v = __ldg(dY + (int64_t)h * ldY + m);
-          if (act_out) v *= act_bwd(__ldg(act_out + (int64_t)h * ldA + m), act);
+      __syncthreads();
+      if (vecA) {
+        for (int u = threadIdx.x; u < BK * (BM / 4); u += 256) {
+          const int hh = u / (BM / 4), q = u % (BM / 4);
+          const int c = c0 + 4 * q, row = s_row[hh];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row >= 0 && c < C) {
+            v = __ldg(reinterpret_cast<const float4 *>(X + (int64_t)row * ldX + c));
+            const float sc = s_scl[hh];
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+          }
+          *reinterpret_cast<float4 *>(&As[hh][4 * q]) = v;
         }
-        Bs[hh][mm] = v;
+      } else {
+        for (int u = threadIdx.x; u < BK * BM; u += 256) {
+          const int hh = u / BM, cc = u % BM;
+          const int c = c0 + cc, row = s_row[hh];
+          As[hh][cc] = (row >= 0 && c < C) ? __ldg(X + (int64_t)row * ldX + c) * s_scl[hh] : 0.f;
+        }
+      }
+      if (vecB) {
+        for (int u = threadIdx.x; u < BK * (BN / 4); u += 256) {
+          const int hh = u / (BN / 4), q = u % (BN / 4);
+          const int h = h0 + hh, m = m0 + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (h < hend && m < M) {
+            v = __ldg(reinterpret_cast<const float4 *>(dY + (int64_t)h * ldY + m));
+            if (act_out) {
+              const float4 a = __ldg(reinterpret_cast<const float4 *>(act_out + (int64_t)h * ldA + m));
+              v.x *= act_bwd(a.x, act); v.y *= act_bwd(a.y, act); v.z *= act_bwd(a.z, act); v.w *= act_bwd(a.w, act);
+            }
+          }
+          *reinterpret_cast<float4 *>(&Bs[hh][4 * q]) = v;
+        }
+      } else {
+        for (int u = threadIdx.x; u < BK * BN; u += 256) {
+          const int hh = u / BN, mm = u % BN;
+          const int h = h0 + hh, m = m0 + mm;
+          float v = 0.f;
+          if (h < hend && m < M) {
+            v = __ldg(dY + (int64_t)h * ldY + m);
+            if (act_out) v *= act_bwd(__ldg(act_out + (int64_t)h * ldA + m), act);
+          }
+          Bs[hh][mm] = v;
+        }
       }
       __syncthreads();
       T.mma(As, Bs);
@@ -478,12 +517,12 @@ k_wgrad(const float *__restrict__ X, int64_t ldX, int C, const float *__restrict
     const int tx = threadIdx.x % T.TX, ty = threadIdx.x / T.TX;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-      const int k = k0 + ty * TM + i;
-      if (k >= K) continue;
+      const int c = c0 + ty * TM + i;
+      if (c >= C) continue;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         const int m = m0 + tx * TN + j;
-        if (m < M) atomicAdd(dWt + (int64_t)k * M + m, T.acc[i][j]);
+        if (m < M) atomicAdd(dWt + (int64_t)(f * C + c) * M + m, T.acc[i][j]);
       }
     }
     if (dbias && blockIdx.y == 0 && threadIdx.x < BN && m0 + threadIdx.x < M) atomicAdd(dbias + m0 + threadIdx.x, bsum);
@@ -650,7 +689,7 @@ extern "C" int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const flo
     constexpr int BM = 64, BN = 64;
     int gx = (int)((h + kWgradChunk - 1) / kWgradChunk);
     if (gx > 1024) gx = 1024;
-    dim3 grid(gx, (F * C + BM - 1) / BM, (M + BN - 1) / BN);
+    dim3 grid(gx, F * ((C + BM - 1) / BM), (M + BN - 1) / BN);
     k_wgrad<IdxT, BM, BN, 4, 4><<<grid, 256, 0, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev, dY, ldY, act_out,
                                                      ldA, act, M, dWt, dbias);
     EFGH_LAUNCH_CHECK();

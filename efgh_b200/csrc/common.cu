@@ -40,3 +40,18 @@ extern "C" int efgh_device_sm_count(void) {
   }
   return v;
 }
+
+// Strided host <-> device copy of a (rows, cols) float matrix (cudaMemcpy2DAsync): packs one scan's (3,n) cloud /
+// (C,n) feature matrix into its column range of a batch's (3, B*n) / (C, B*n) device matrix with one DMA
+// descriptor per scan instead of a staging buffer + copy kernel.  `kind`: 1 = host -> device, 2 = device -> host.
+extern "C" int efgh_copy_matrix_async(void *dst, int64_t dst_ld, const void *src, int64_t src_ld, int64_t rows,
+                                      int64_t cols, int kind, void *stream) {
+  EFGH_REQUIRE(rows >= 0 && cols >= 0 && dst_ld >= cols && src_ld >= cols, "efgh_copy_matrix_async: bad sizes");
+  EFGH_REQUIRE(kind == 1 || kind == 2, "efgh_copy_matrix_async: kind must be 1 (H2D) or 2 (D2H)");
+  if (rows == 0 || cols == 0) return EFGH_OK;
+  EFGH_REQUIRE(dst && src, "efgh_copy_matrix_async: null pointer");
+  EFGH_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_ld * 4, src, (size_t)src_ld * 4, (size_t)cols * 4, (size_t)rows,
+                                    kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                    static_cast<cudaStream_t>(stream)));
+  return EFGH_OK;
+}

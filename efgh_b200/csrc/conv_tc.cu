@@ -472,13 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
         mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);      // epilogue drained this accumulator stage
         tc_fence_after();
-        // When TMEM has room the three products of 3xTF32 go to separate accumulators that the epilogue adds up with
-        // round-to-nearest adds: d_sb (A_small*B_big), d_bs (A_big*B_small), d_bb (A_big*B_big).  The tensor core
-        // rounds toward zero on every accumulate, so keeping the tiny correction products out of the main chain
-        // shortens it 3x (measured error 1.0e-6 instead of 1.7e-6 per layer).
+        // 3xTF32 = A_big*B_big + A_big*B_small + A_small*B_big.  The weight image holds [big rows | small rows]
+        // back to back, so when TMEM has room for separate accumulators (nacc >= 2) ONE descriptor with N' = 2N
+        // makes A_big*[B_big | B_small] a single MMA writing two adjacent accumulators (bb | bs): 8 MMAs per
+        // chunk instead of 12 - the warp is bound by MMA issue, not by tensor throughput, at these widths.  The
+        // epilogue adds the accumulators with round-to-nearest adds; the tensor core rounds toward zero on every
+        // accumulate, so keeping the tiny correction products out of the main chain also shortens it (measured
+        // error 1.0e-6 instead of 1.7e-6 per layer).
         const uint32_t tmem_d0 = tmem_base + as * (uint32_t)(p.nacc * N);
-        const uint32_t d_bb = tmem_d0 + (uint32_t)((p.nacc - 1) * N);
-        const uint32_t d_sb = tmem_d0, d_bs = tmem_d0 + (uint32_t)((p.nacc == 3 ? 1 : 0) * N);
+        const uint32_t d_sb = tmem_d0 + (uint32_t)((p.nacc == 3 ? 2 : 1) * N);   // nacc 2: shares the bs accumulator
+        const uint32_t idesc2 = make_idesc(2 * N);
         for (int j = j_begin; j < j_end; ++j) {
           const uint32_t team = seq++ & (kTeams - 1);
           mbar_wait(bar_a_full + 8 * team, (pha_bits >> team) & 1);
@@ -490,18 +493,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           const uint32_t b_big = smem_base + sb * b_bytes, b_small = b_big + (uint32_t)N * 128u;
           const uint64_t dbb = make_desc(b_big);
           const uint32_t first = j == j_begin;
-          if (NSPLIT == 3) {
-            const uint64_t dbs = make_desc(b_small);
-            // interleave the chains so that back-to-back MMAs never target the same accumulator
+          if (NSPLIT == 3 && p.nacc >= 2) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts(d_sb, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
-              umma_tf32_ts(d_bs, a_big + 8 * k4, dbs + 2 * k4, idesc, !(first && k4 == 0 && p.nacc == 3));
-              umma_tf32_ts(d_bb, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0 && p.nacc >= 2));
+              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc2, !(first && k4 == 0));
+              umma_tf32_ts(d_sb, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0 && p.nacc == 3));
+            }
+          } else if (NSPLIT == 3) {
+            const uint64_t dbs = make_desc(b_small);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ts(tmem_d0, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
+              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbs + 2 * k4, idesc, 1);
+              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc, 1);
             }
           } else {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(d_bb, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
+            for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
           }
           umma_commit(bar_a_empty + 8 * team);               // frees the team's TMEM A stage when these MMAs retire
           umma_commit(bar_b_empty + 8 * sb);                 // ... and the weight stage

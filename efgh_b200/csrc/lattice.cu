@@ -43,6 +43,34 @@ struct __align__(16) Entry {
   int index;
 };
 
+// Several scans in one launch sequence ("ragged batch").  The point streams of B scans are
+// concatenated (scan b = points [pt_start[b], pt_start[b+1])); every scan keeps its OWN hash table (region b of
+// `tstride` entries), its own key box and its own insertion order, so per scan the result is what the single-scan
+// path produces - only the vertex indices are global: vertex_start[b] + local index.  The kernels downstream (splat,
+// convolution) then treat the batch as one big lattice.  info (int32, device):
+//   [0, B]                vertex_start (written by k_assign; it is the next level's pt_start)
+//   [tm_off, tm_off + B)  per-scan table mask
+//   [box_off + 8 b ...)   per-scan key box: min[4], max[4]   (one 32-byte sector per scan)
+constexpr int kMaxBatch = 64;
+struct Batch {
+  const int32_t *pt_start;   // nullptr = single scan
+  int32_t *info;
+  int B, tm_off, box_off;
+  long long tstride;
+};
+inline int batch_tm_off(int B) { return (B + 1 + 7) & ~7; }
+inline int batch_box_off(int B) { return batch_tm_off(B) + ((B + 7) & ~7); }
+
+// scan that owns stream element i: largest b with start[b] <= i (start[] ascending, start[0] = 0)
+__device__ __forceinline__ int find_scan(const int *start, int B, int i) {
+  int lo = 0, hi = B;                                   // invariant: start[lo] <= i < start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (start[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 struct Workspace {
   Entry *table;
   int4 *slots;
@@ -60,13 +88,15 @@ inline int64_t pow2_ceil(int64_t v) {
 
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-Workspace carve(void *base, int64_t n_cap) {
+// n_cap: points of the whole launch; B scans of at most n_cap_scan points each (B = 1: n_cap_scan = n_cap)
+Workspace carve(void *base, int64_t n_cap, int B = 1, int64_t n_cap_scan = -1) {
   Workspace w;
   if (n_cap < 1) n_cap = 1;
-  w.table_cap = pow2_ceil(8 * n_cap);
+  if (n_cap_scan < 1) n_cap_scan = n_cap;
+  w.table_cap = pow2_ceil(8 * n_cap_scan);               // per scan
   size_t off = 0;
   char *b = static_cast<char *>(base);
-  w.table = reinterpret_cast<Entry *>(b + off); off = align_up(off + sizeof(Entry) * w.table_cap);
+  w.table = reinterpret_cast<Entry *>(b + off); off = align_up(off + sizeof(Entry) * w.table_cap * B);
   w.slots = reinterpret_cast<int4 *>(b + off); off = align_up(off + sizeof(int4) * n_cap);
   w.vkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * 4 * n_cap);
   w.tiles = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * ((n_cap + kTile - 1) / kTile + 1));
@@ -103,13 +133,25 @@ __device__ __forceinline__ int table_mask_for(int n, int64_t table_cap) {
 }
 
 __global__ void k_clear(efgh_lattice_state *st, const int32_t *n_dev, int n_host, int64_t table_cap,
-                        Entry *table, unsigned long long *tiles, int n_tiles_cap) {
-  int n = n_dev ? min(max(*n_dev, 0), n_host) : n_host;
-  int mask = table_mask_for(n, table_cap);
+                        Entry *table, unsigned long long *tiles, int n_tiles_cap, Batch bt) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int4 empty = make_int4(-1, -1, 0x7fffffff, -1);   // key = ~0, first_pos = INT_MAX, index = -1
-  for (int64_t i = tid; i <= mask; i += stride) reinterpret_cast<int4 *>(table)[i] = empty;
+  int n, mask = 0;
+  if (bt.pt_start) {
+    n = min(max(bt.pt_start[bt.B], 0), n_host);
+    for (int b = 0; b < bt.B; ++b) {
+      const int mb = table_mask_for(bt.pt_start[b + 1] - bt.pt_start[b], table_cap);
+      Entry *tb = table + (long long)b * bt.tstride;
+      for (int64_t i = tid; i <= mb; i += stride) reinterpret_cast<int4 *>(tb)[i] = empty;
+      if (tid == 0) bt.info[bt.tm_off + b] = mb;
+      if (tid < 8) bt.info[bt.box_off + 8 * b + tid] = tid < 4 ? 0x7fffffff : -0x7fffffff - 1;
+    }
+  } else {
+    n = n_dev ? min(max(*n_dev, 0), n_host) : n_host;
+    mask = table_mask_for(n, table_cap);
+    for (int64_t i = tid; i <= mask; i += stride) reinterpret_cast<int4 *>(table)[i] = empty;
+  }
   int n_tiles = (n + kTile - 1) / kTile;
   for (int64_t i = tid; i < n_tiles && i < n_tiles_cap; i += stride) tiles[i] = 0ull;
   if (tid == 0) {
@@ -138,19 +180,39 @@ __device__ __forceinline__ int canonical(int i, int j) { return (j <= 3 - i) ? j
 
 __global__ void __launch_bounds__(kPointThreads)
 k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__restrict__ bary,
-         float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, Entry *table, int4 *slots) {
+         float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, Entry *table_all, int4 *slots, Batch bt) {
   const int n = st->n;
-  const unsigned mask = (unsigned)st->table_mask;
+  unsigned mask = (unsigned)st->table_mask;
+  Entry *table = table_all;
   int kmin[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
   int kmax[4] = {-0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1};
   int bad = 0;
+  __shared__ int s_start[kMaxBatch + 1];
+  __shared__ int s_min[4][kPointThreads / 32], s_max[4][kPointThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool batched = bt.pt_start != nullptr;
+  if (batched) {
+    for (int b = threadIdx.x; b <= bt.B; b += blockDim.x) s_start[b] = bt.pt_start[b];
+    __syncthreads();
+  }
 
   const float E[4][3] = {{EFGH_E_A, EFGH_E_B, EFGH_E_C},
                          {-EFGH_E_A, EFGH_E_B, EFGH_E_C},
                          {0.0f, EFGH_E_B2, EFGH_E_C},
                          {0.0f, 0.0f, EFGH_E_C3}};
 
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // (the loop is CTA-uniform - every thread runs the same number of rounds - because the batched path ends each
+  //  round with a CTA-wide key-box reduction)
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    int scan = 0;
+    if (batched) {
+      scan = find_scan(s_start, bt.B, min(i, n - 1));
+      table = table_all + (long long)scan * bt.tstride;
+      mask = (unsigned)bt.info[bt.tm_off + scan];
+    }
+    const long long slot_base = (long long)scan * bt.tstride;
+    if (i < n) {
     float p[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) p[a] = __fmul_rn(__ldg(pts + a * pts_ld + i), scale);  // generate_data.py:130
@@ -238,14 +300,51 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
         if (cur == kEmpty) cur = atomicCAS(&table[h].key, kEmpty, key);
       }
       atomicMin(&table[h].first_pos, 4 * i + r);
-      s4[r] = (int)h;
+      s4[r] = (int)(slot_base + h);
     }
     slots[i] = make_int4(s4[0], s4[1], s4[2], s4[3]);
+    }  // i < n
+
+    if (batched) {
+      // per-scan key box.  Almost every CTA round lies inside one scan: CTA reduction, 8 guarded atomics.  A round
+      // that straddles a scan boundary (at most B - 1 of them per launch) falls back to guarded per-thread atomics.
+      const int first = find_scan(s_start, bt.B, min(base, n - 1));
+      const int last = find_scan(s_start, bt.B, min(base + (int)blockDim.x - 1, n - 1));
+      if (first == last) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int mn = warp_reduce_min(kmin[c]), mx = warp_reduce_max(kmax[c]);
+          if (lane == 0) { s_min[c][wid] = mn; s_max[c][wid] = mx; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+          int c = threadIdx.x, mn = s_min[c][0], mx = s_max[c][0];
+          for (int w = 1; w < kPointThreads / 32; ++w) { mn = min(mn, s_min[c][w]); mx = max(mx, s_max[c][w]); }
+          int *box = bt.info + bt.box_off + 8 * first;
+          if (mn <= mx) {
+            if (mn < *(volatile int *)&box[c]) atomicMin(&box[c], mn);
+            if (mx > *(volatile int *)&box[4 + c]) atomicMax(&box[4 + c], mx);
+          }
+        }
+        __syncthreads();
+      } else if (i < n) {
+        int *box = bt.info + bt.box_off + 8 * scan;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (kmin[c] < *(volatile int *)&box[c]) atomicMin(&box[c], kmin[c]);
+          if (kmax[c] > *(volatile int *)&box[4 + c]) atomicMax(&box[4 + c], kmax[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kmin[c] = 0x7fffffff; kmax[c] = -0x7fffffff - 1; }
+    }
   }
 
+  if (batched) {
+    if (bad) atomicOr(&st->status, (bad & 1 ? EFGH_ST_KEY_RANGE : 0) | (bad & 4 ? EFGH_ST_TABLE_FULL : 0));
+    return;
+  }
   // key box: warp shuffle -> shared -> 8 global atomics per CTA
-  __shared__ int s_min[4][kPointThreads / 32], s_max[4][kPointThreads / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     int mn = warp_reduce_min(kmin[c]), mx = warp_reduce_max(kmax[c]);
@@ -272,7 +371,7 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
 constexpr int kAssignThreads = kTile / 2;
 __global__ void __launch_bounds__(kAssignThreads)
 k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
-         unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap) {
+         unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap, Batch bt) {
   __shared__ int s_tile, s_prefix;
   __shared__ int s_warp[kAssignThreads / 32];
   const int n = st->n;
@@ -357,12 +456,22 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
       if (tile == n_tiles - 1) {
         const int total = prefix + block_total;
         st->hash_cnt = total;
+        if (bt.pt_start) bt.info[bt.B] = total;             // vertex_start[B]
         if (total > h_cap) atomicOr(&st->status, EFGH_ST_VERTEX_CAP);
       }
     }
   }
   __syncthreads();
   int idx = s_prefix + local;
+  if (bt.pt_start) {
+    // vertex_start[b] = number of vertices created before scan b's first point (scans are never empty)
+    const int c0 = fl[0] + fl[1] + fl[2] + fl[3];
+    for (int b = 0; b < bt.B; ++b) {
+      const int ps = bt.pt_start[b];
+      if (ps == i0) bt.info[b] = idx;
+      else if (ps == i0 + 1) bt.info[b] = idx + c0;
+    }
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e)
     if (fl[e]) { table[sl[e]].index = idx; vkeys[idx] = kk[e]; ++idx; }
@@ -387,21 +496,29 @@ __device__ __forceinline__ long long floor_mod64(long long a, long long b) {
 
 __global__ void __launch_bounds__(256)
 k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
-           const Entry *__restrict__ table, const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
+           const Entry *__restrict__ table_all, const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
            int64_t off_ld, const int32_t *__restrict__ foffs, int F, int64_t *__restrict__ nbr,
            int32_t *__restrict__ nbr32, int64_t nbr_ld, float *__restrict__ next_pts, int64_t next_ld,
-           float next_divisor) {
+           float next_divisor, Batch bt) {
   const int n = min(st->n, n_cap);
   const int H = min(st->hash_cnt, h_cap);
-  const unsigned mask = (unsigned)st->table_mask;
+  unsigned mask = (unsigned)st->table_mask;
   const int stride = gridDim.x * blockDim.x;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_start[kMaxBatch + 1];
+  const bool batched = bt.pt_start != nullptr;
+  if (batched) {
+    for (int b = threadIdx.x; b <= bt.B; b += blockDim.x) s_start[b] = bt.info[b];    // vertex_start
+    __syncthreads();
+  }
 
+  const Entry *table = table_all;
   // lattice offsets: pc1_lattice_offset[r, n] = vertex index of the point's r-th key (transforms.py:166)
+  // (slots are global table positions, so this part is the same for one scan and for a batch)
   if (loff || loff32) {
     for (int i = tid; i < n; i += stride) {
       const int4 s = slots[i];
-      const int v0 = table[s.x].index, v1 = table[s.y].index, v2 = table[s.z].index, v3 = table[s.w].index;
+      const int v0 = table_all[s.x].index, v1 = table_all[s.y].index, v2 = table_all[s.z].index, v3 = table_all[s.w].index;
       if (loff) {
         loff[i] = v0; loff[off_ld + i] = v1; loff[2 * off_ld + i] = v2; loff[3 * off_ld + i] = v3;
       }
@@ -424,11 +541,19 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
   const bool want_nbr = F > 0 && (nbr || nbr32);
   const int groups = want_nbr ? 4 : 1;
   const long long total = (long long)groups * H;
-  const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
-                  s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
   for (long long item = tid; item < total; item += stride) {
     const int g = (int)(item / H);
     const int h = (int)(item - (long long)g * H);
+    if (batched) {                                             // the vertex's own scan: its table, its key box
+      const int scan = find_scan(s_start, bt.B, h);
+      table = table_all + (long long)scan * bt.tstride;
+      mask = (unsigned)bt.info[bt.tm_off + scan];
+      const int *box = bt.info + bt.box_off + 8 * scan;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kmin[c] = box[c]; kmax[c] = box[4 + c]; }
+    }
+    const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
+                    s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
     int k[4];
     unpack_key(vkeys[h], k[0], k[1], k[2]);
     k[3] = -(k[0] + k[1] + k[2]);
@@ -514,48 +639,61 @@ using namespace efgh;
 
 extern "C" size_t efgh_lattice_workspace_bytes(int64_t n_cap) { return carve(nullptr, n_cap).bytes; }
 
-extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
-                                   float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap,
-                                   efgh_lattice_state *state, void *workspace, size_t workspace_bytes,
-                                   void *stream) {
-  EFGH_REQUIRE(n >= 0 && n < (1ll << 28), "efgh_lattice_points: n=%lld out of range", (long long)n);
-  EFGH_REQUIRE(state && workspace && (n == 0 || (pts && barycentric && el_minus_gr)), "efgh_lattice_points: null pointer");
-  EFGH_REQUIRE(pts_ld >= n && out_ld >= n, "efgh_lattice_points: leading dimension smaller than n");
-  Workspace w = carve(workspace, n);
+extern "C" size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, int64_t n_cap_total) {
+  if (B < 1) B = 1;
+  return carve(nullptr, n_cap_total, B, n_cap_scan).bytes;
+}
+
+extern "C" int64_t efgh_lattice_batch_info_ints(int B) { return B < 1 ? 0 : (int64_t)batch_box_off(B) + 8 * (int64_t)B; }
+
+namespace {
+
+int lattice_points_impl(const char *who, const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
+                        float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap, efgh_lattice_state *state,
+                        void *workspace, size_t workspace_bytes, void *stream, Batch bt, int64_t n_cap_scan) {
+  EFGH_REQUIRE(n >= 0 && n < (1ll << 28), "%s: n=%lld out of range", who, (long long)n);
+  EFGH_REQUIRE(state && workspace && (n == 0 || (pts && barycentric && el_minus_gr)), "%s: null pointer", who);
+  EFGH_REQUIRE(pts_ld >= n && out_ld >= n, "%s: leading dimension smaller than n", who);
+  const int B = bt.pt_start ? bt.B : 1;
+  Workspace w = carve(workspace, n, B, bt.pt_start ? n_cap_scan : n);
   if (w.bytes > workspace_bytes) {
-    set_error("efgh_lattice_points: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, w.bytes);
     return EFGH_ENOMEM;
   }
+  EFGH_REQUIRE(w.table_cap * B < (1ll << 31), "%s: hash tables of the batch exceed 2^31 entries", who);
+  bt.tstride = w.table_cap;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n_tiles_cap = (int)((n + kTile - 1) / kTile) + 1;
-  k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.table, w.tiles, n_tiles_cap);
+  k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.table, w.tiles, n_tiles_cap, bt);
   EFGH_LAUNCH_CHECK();
   if (n == 0) return EFGH_OK;
   k_points<<<grid_for(n, kPointThreads, 8), kPointThreads, 0, s>>>(pts, pts_ld, scale, barycentric, el_minus_gr,
-                                                                   out_ld, state, w.table, w.slots);
+                                                                   out_ld, state, w.table, w.slots, bt);
   EFGH_LAUNCH_CHECK();
   k_assign<<<(int)((n + kTile - 1) / kTile), kAssignThreads, 0, s>>>(state, w.slots, w.table, w.vkeys, w.tiles,
-                                                            (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30)));
+                                                            (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30)), bt);
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
 }
 
-extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
-                                     const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
-                                     int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
-                                     float next_divisor, efgh_lattice_state *state, void *workspace,
-                                     size_t workspace_bytes, void *stream) {
-  EFGH_REQUIRE(n >= 0 && n < (1ll << 28) && h >= 0 && h < (1ll << 30), "efgh_lattice_vertices: sizes out of range");
-  EFGH_REQUIRE(state && workspace, "efgh_lattice_vertices: null pointer");
-  EFGH_REQUIRE(F <= 0 || filter_offsets, "efgh_lattice_vertices: filter_offsets is null");
-  EFGH_REQUIRE((!lattice_offset && !lattice_offset32) || off_ld >= n, "efgh_lattice_vertices: off_ld < n");
-  EFGH_REQUIRE((!blur_neighbors && !blur_neighbors32) || nbr_ld >= h, "efgh_lattice_vertices: nbr_ld < h");
-  EFGH_REQUIRE(!next_pts || next_ld >= h, "efgh_lattice_vertices: next_ld < h");
-  Workspace w = carve(workspace, n);
+int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                          const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
+                          int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld, float next_divisor,
+                          efgh_lattice_state *state, void *workspace, size_t workspace_bytes, void *stream, Batch bt,
+                          int64_t n_cap_scan) {
+  EFGH_REQUIRE(n >= 0 && n < (1ll << 28) && h >= 0 && h < (1ll << 30), "%s: sizes out of range", who);
+  EFGH_REQUIRE(state && workspace, "%s: null pointer", who);
+  EFGH_REQUIRE(F <= 0 || filter_offsets, "%s: filter_offsets is null", who);
+  EFGH_REQUIRE((!lattice_offset && !lattice_offset32) || off_ld >= n, "%s: off_ld < n", who);
+  EFGH_REQUIRE((!blur_neighbors && !blur_neighbors32) || nbr_ld >= h, "%s: nbr_ld < h", who);
+  EFGH_REQUIRE(!next_pts || next_ld >= h, "%s: next_ld < h", who);
+  const int B = bt.pt_start ? bt.B : 1;
+  Workspace w = carve(workspace, n, B, bt.pt_start ? n_cap_scan : n);
   if (w.bytes > workspace_bytes) {
-    set_error("efgh_lattice_vertices: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, w.bytes);
     return EFGH_ENOMEM;
   }
+  bt.tstride = w.table_cap;
   if (n == 0) return EFGH_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t vitems = h * (F > 0 ? 4 : 1);
@@ -563,7 +701,60 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
   k_vertices<<<grid_for(items, 256, 8), 256, 0, s>>>(state, (int)n, (int)h, w.slots, w.table, w.vkeys,
                                                      lattice_offset, lattice_offset32, off_ld, filter_offsets, F,
                                                      blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
-                                                     next_divisor);
+                                                     next_divisor, bt);
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;
+}
+
+int make_batch(const char *who, const int32_t *scan_start, int B, int64_t n_cap_scan, int32_t *batch_info, Batch *bt) {
+  EFGH_REQUIRE(B >= 1 && B <= kMaxBatch, "%s: batch of %d scans (1..%d supported)", who, B, kMaxBatch);
+  EFGH_REQUIRE(scan_start && batch_info && n_cap_scan >= 1, "%s: null scan_start / batch_info or n_cap_scan < 1", who);
+  bt->pt_start = scan_start; bt->info = batch_info; bt->B = B;
+  bt->tm_off = batch_tm_off(B); bt->box_off = batch_box_off(B); bt->tstride = 0;
+  return EFGH_OK;
+}
+
+}  // namespace
+
+extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
+                                   float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap,
+                                   efgh_lattice_state *state, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+  Batch bt = {nullptr, nullptr, 1, 0, 0, 0};
+  return lattice_points_impl("efgh_lattice_points", pts, pts_ld, n, n_dev, scale, barycentric, el_minus_gr, out_ld, h_cap,
+                             state, workspace, workspace_bytes, stream, bt, n);
+}
+
+extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                                     const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
+                                     int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
+                                     float next_divisor, efgh_lattice_state *state, void *workspace,
+                                     size_t workspace_bytes, void *stream) {
+  Batch bt = {nullptr, nullptr, 1, 0, 0, 0};
+  return lattice_vertices_impl("efgh_lattice_vertices", n, lattice_offset, lattice_offset32, off_ld, filter_offsets, F, h,
+                               blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld, next_divisor, state, workspace,
+                               workspace_bytes, stream, bt, n);
+}
+
+extern "C" int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start,
+                                         int B, int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr,
+                                         int64_t out_ld, int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info,
+                                         void *workspace, size_t workspace_bytes, void *stream) {
+  Batch bt;
+  if (int rc = make_batch("efgh_lattice_points_batch", scan_start, B, n_cap_scan, batch_info, &bt)) return rc;
+  return lattice_points_impl("efgh_lattice_points_batch", pts, pts_ld, n_cap_total, nullptr, scale, barycentric,
+                             el_minus_gr, out_ld, h_cap, state, workspace, workspace_bytes, stream, bt, n_cap_scan);
+}
+
+extern "C" int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t n_cap_scan,
+                                           int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                                           const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
+                                           int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
+                                           float next_divisor, efgh_lattice_state *state, int32_t *batch_info,
+                                           void *workspace, size_t workspace_bytes, void *stream) {
+  Batch bt;
+  if (int rc = make_batch("efgh_lattice_vertices_batch", scan_start, B, n_cap_scan, batch_info, &bt)) return rc;
+  return lattice_vertices_impl("efgh_lattice_vertices_batch", n_cap_total, lattice_offset, lattice_offset32, off_ld,
+                               filter_offsets, F, h, blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
+                               next_divisor, state, workspace, workspace_bytes, stream, bt, n_cap_scan);
 }

@@ -13,8 +13,14 @@ build (reference nets/generate_data.py:117-193) followed by the five BilateralCo
   * the reference-format int64 tensors (pc1_lattice_offset, pc1_blur_neighbors) are still produced - they
     are part of the lattice build's contract - next to int32 copies that the BCL kernels read.
 
-Several pipelines on different CUDA streams run concurrently (one scan each); scans are independent
-(SURVEY.md §8e), which is also how they shard across GPUs.
+Several pipelines on different CUDA streams run concurrently; scans are independent, which is
+also how they shard across GPUs.
+
+`batch=B` ("ragged batched lattices"): B scans go through ONE launch sequence.  Their point
+streams are concatenated, every scan keeps its own hash table / key box / insertion order
+(efgh_lattice_*_batch), vertex indices are global, and the splat / convolution kernels see one big lattice.
+The ~55 launches and, more importantly, the latency-bound small kernels of the coarse levels (a few thousand
+vertices each) are paid once per batch instead of once per scan.
 """
 import numpy as np
 import torch
@@ -28,14 +34,19 @@ _ACT = {"none": 0, "relu": 1, "leaky": 2}
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
                  vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
-                 precision="3xtf32"):
+                 precision="3xtf32", batch=1):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
         vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
-        precision: "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05, one pass) or "fp32" (CUDA cores)."""
+        precision: "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05, one pass) or "fp32" (CUDA cores);
+        batch: scans per launch sequence, each of n_points points (inputs are then (3, batch*n_points) /
+        (C, batch*n_points), scan b in columns [b*n_points, (b+1)*n_points))."""
         self.dev = torch.device(device)
         self.L = _capi.lib()
-        self.n0 = int(n_points)
+        self.B = int(batch)
+        assert 1 <= self.B <= 64
+        self.n_scan = int(n_points)
+        self.n0 = int(n_points) * self.B
         self.smap = scales_filter_map
         self.plan = bcl_plan
         self.nlev = len(scales_filter_map)
@@ -52,8 +63,10 @@ class ScanPipeline(object):
         dev = self.dev
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
         cap = max(int(vertex_cap_factor * self.n0), 1024)
+        cap_scan = max(int(vertex_cap_factor * self.n_scan), 1024)     # one scan's share: sizes its hash table
         self.levels = []
         n_cap = self.n0
+        n_cap_scan = self.n_scan
         prev_c = stem_channels
         with torch.cuda.device(dev):
             self.states = torch.zeros((self.nlev, STATE_WORDS), dtype=i32, device=dev)
@@ -65,6 +78,8 @@ class ScanPipeline(object):
                 F = self.gd.get_filter_size(radius)
                 h_cap = min(4 * n_cap, cap)
                 lv = {
+                    "n_cap_scan": n_cap_scan,
+                    "info": torch.zeros(max(int(self.L.efgh_lattice_batch_info_ints(self.B)), 1), dtype=i32, device=dev),
                     "n_cap": n_cap, "h_cap": h_cap, "F": F, "scale": float(scale), "cin": cin, "cmid": cmid, "cout": cout,
                     "divisor": float(np.float32(self.gd.expected_std * scale)),
                     "offs": torch.from_numpy(self.gd.radius2offset[radius].astype(np.int32)).to(dev),
@@ -97,14 +112,32 @@ class ScanPipeline(object):
                                                                  torch.cuda.current_stream(dev).cuda_stream), "efgh_bcl_pack_weights")
                         lv[nm] = img
                     lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin) > 1
-                ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
+                if self.B > 1:
+                    ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, n_cap_scan, n_cap))
+                else:
+                    ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
                 self.levels.append(lv)
                 n_cap = h_cap
+                n_cap_scan = min(4 * n_cap_scan, cap_scan)
                 prev_c = cout
             self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            self._starts0 = [b * self.n_scan for b in range(self.B + 1)]
+            self.scan_start = torch.tensor(self._starts0, dtype=i32, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
         self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 1 + 2)
+
+    def set_scan_sizes(self, sizes):
+        """Batched pipelines: ragged batch - scan b has sizes[b] (1 <= sizes[b] <= n_points) points, stored back to
+        back in the (3, B*n_points) / (C, B*n_points) inputs.  Synchronising (rewrites a device array that enqueued
+        work may still read); previously captured graphs stay valid (they read the same array)."""
+        assert self.B > 1 and len(sizes) == self.B and all(1 <= int(v) <= self.n_scan for v in sizes)
+        torch.cuda.synchronize(self.dev)
+        self._starts0 = [0]
+        for v in sizes:
+            self._starts0.append(self._starts0[-1] + int(v))
+        self.scan_start.copy_(torch.tensor(self._starts0, dtype=torch.int32))
+        torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------
     def enqueue(self, pc, feat0, stream=None, timers=None):
@@ -144,17 +177,31 @@ class ScanPipeline(object):
         pts_ptr, pts_ld = pc.data_ptr(), pc.stride(0)
         prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
         n_dev = None
+        seg = self.scan_start.data_ptr()                      # batched: point-stream boundaries of the level
+        if self.B > 1:
+            n_dev = seg + 4 * self.B                          # total points of a (possibly ragged) batch
         for li, lv in enumerate(self.levels):
             st = self.states[li].data_ptr()
             n_cap, h_cap, cin = lv["n_cap"], lv["h_cap"], lv["cin"]
             h_dev = st + 4           # &state.hash_cnt
-            timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points(
-                pts_ptr, pts_ld, n_cap, n_dev, lv["scale"], lv["bary"].data_ptr(), lv["elmgr"].data_ptr(), n_cap, h_cap,
-                st, ws, wsn, s_lat), "efgh_lattice_points"))
-            timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices(
-                n_cap, _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap, lv["offs"].data_ptr(), lv["F"], h_cap,
-                _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
-                st, ws, wsn, s_lat), "efgh_lattice_vertices"))
+            if self.B > 1:
+                info = lv["info"].data_ptr()
+                timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points_batch(
+                    pts_ptr, pts_ld, n_cap, seg, self.B, lv["n_cap_scan"], lv["scale"], lv["bary"].data_ptr(),
+                    lv["elmgr"].data_ptr(), n_cap, h_cap, st, info, ws, wsn, s_lat), "efgh_lattice_points_batch"))
+                timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices_batch(
+                    n_cap, seg, self.B, lv["n_cap_scan"], _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap,
+                    lv["offs"].data_ptr(), lv["F"], h_cap, _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap,
+                    _capi.ptr(lv["next"]), h_cap, lv["divisor"], st, info, ws, wsn, s_lat), "efgh_lattice_vertices_batch"))
+                seg = info                                    # vertex_start of this level = scan_start of the next
+            else:
+                timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points(
+                    pts_ptr, pts_ld, n_cap, n_dev, lv["scale"], lv["bary"].data_ptr(), lv["elmgr"].data_ptr(), n_cap, h_cap,
+                    st, ws, wsn, s_lat), "efgh_lattice_points"))
+                timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices(
+                    n_cap, _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap, lv["offs"].data_ptr(), lv["F"], h_cap,
+                    _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap, _capi.ptr(lv["next"]), h_cap, lv["divisor"],
+                    st, ws, wsn, s_lat), "efgh_lattice_vertices"))
             S = lv["S"].data_ptr()
             zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
             # zero-fill of this level's accumulators: on the lattice stream, i.e. off the BCL chain's critical path
@@ -216,14 +263,26 @@ class ScanPipeline(object):
             self._graphs[key] = g
         return g
 
-    def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None, use_graph=False):
+    def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None, use_graph=False, starts_host=None):
         """End-to-end call on HOST buffers (pinned for async copies): H2D of the cloud and stem features,
         the whole scan, D2H of the level records and of the first out_host.shape[0] rows of the last
-        level's output.  Everything is enqueued on `stream`; synchronise it before reading the outputs."""
+        level's output.  Everything is enqueued on `stream`; synchronise it before reading the outputs.
+        Batched pipelines take lists of B per-scan host tensors ((3,n) / (C,n) each) - or one (3, B*n) / (C, B*n)
+        tensor already in batch layout - and, if given, fill starts_host (nlev, B+1) int32 with every level's
+        per-scan vertex boundaries."""
         st = stream if stream is not None else torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(st):
-            self._pc_dev.copy_(pc_host, non_blocking=True)
-            self._feat_dev.copy_(feat_host, non_blocking=True)
+            if isinstance(pc_host, (list, tuple)):
+                n = self.n_scan
+                for b in range(self.B):                     # one strided DMA per matrix (no staging buffer)
+                    for dst, src in ((self._pc_dev, pc_host[b]), (self._feat_dev, feat_host[b])):
+                        assert src.is_contiguous() and src.dtype == torch.float32 and src.shape[1] <= n
+                        _capi.check(self.L.efgh_copy_matrix_async(dst.data_ptr() + 4 * self._starts0[b], dst.stride(0),
+                                                                  src.data_ptr(), src.shape[1], src.shape[0], src.shape[1],
+                                                                  1, st.cuda_stream), "efgh_copy_matrix_async")
+            else:
+                self._pc_dev.copy_(pc_host, non_blocking=True)
+                self._feat_dev.copy_(feat_host, non_blocking=True)
             if use_graph:
                 self.graph_for(self._pc_dev, self._feat_dev, st).replay()
                 Z = self.levels[-1]["Z"]
@@ -231,6 +290,9 @@ class ScanPipeline(object):
                 Z = self.enqueue(self._pc_dev, self._feat_dev, stream=st)
             out_host.copy_(Z[:out_host.shape[0]], non_blocking=True)
             state_host.copy_(self.states, non_blocking=True)
+            if starts_host is not None:
+                for li, lv in enumerate(self.levels):
+                    starts_host[li].copy_(lv["info"][:self.B + 1], non_blocking=True)
         return out_host, state_host
 
     def counts(self):
@@ -242,9 +304,29 @@ class ScanPipeline(object):
             check_status(int(host[li, 2]), li)
         return [int(host[li, 1]) for li in range(self.nlev)]
 
-    def level_dicts(self):
-        """The reference-format per-level dicts (views of the pipeline's buffers) of the last scan."""
+    def vertex_starts(self):
+        """Batched mode: per level, the (B+1) global vertex boundaries of the scans (synchronising read)."""
+        return [lv["info"][:self.B + 1].cpu().tolist() if self.B > 1 else [0, c]
+                for lv, c in zip(self.levels, self.counts())]
+
+    def level_dicts(self, scan=None):
+        """The reference-format per-level dicts of the last scan (views of the pipeline's buffers).  Batched
+        pipelines: pass `scan=b` to get scan b's dicts with LOCAL vertex indices, i.e. what a single-scan build
+        of that cloud returns (copies, not views)."""
         cnt = self.counts()
+        if self.B > 1:
+            assert scan is not None, "batched pipeline: level_dicts(scan=b)"
+            vs = self.vertex_starts()
+            out, p0, p1 = [], self._starts0[scan], self._starts0[scan + 1]
+            for li, lv in enumerate(self.levels):
+                v0, v1 = vs[li][scan], vs[li][scan + 1]
+                lo = (lv["loff64"] if self.emit_int64 else lv["loff32"])[:, p0:p1] - v0
+                nb = (lv["nbr64"] if self.emit_int64 else lv["nbr32"])[:, v0:v1]
+                nb = torch.where(nb >= 0, nb - v0, nb)
+                out.append({"pc1_barycentric": lv["bary"][None, :, p0:p1], "pc1_el_minus_gr": lv["elmgr"][None, :, p0:p1],
+                            "pc1_lattice_offset": lo[None], "pc1_blur_neighbors": nb[None], "pc1_hash_cnt": v1 - v0})
+                p0, p1 = v0, v1
+            return out
         out, n = [], self.n0
         for li, lv in enumerate(self.levels):
             H = cnt[li]
@@ -255,9 +337,13 @@ class ScanPipeline(object):
             n = H
         return out
 
-    def outputs(self):
-        """[(1, C_out, H_l) views] - what bcn1..bcn5 return in reference enet.py:113-141."""
+    def outputs(self, scan=None):
+        """[(1, C_out, H_l) views] - what bcn1..bcn5 return in reference enet.py:113-141 (batched: of scan `scan`)."""
         cnt = self.counts()
+        if self.B > 1:
+            assert scan is not None, "batched pipeline: outputs(scan=b)"
+            vs = self.vertex_starts()
+            return [lv["Z"][vs[li][scan]:vs[li][scan + 1]].t()[None] for li, lv in enumerate(self.levels)]
         return [lv["Z"][:cnt[li]].t()[None] for li, lv in enumerate(self.levels)]
 
     # ------------------------------------------------------------------------------------------

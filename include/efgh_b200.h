@@ -63,6 +63,12 @@ int efgh_version(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int efgh_device_sm_count(void);
 
+/* Strided host <-> device copy of a (rows, cols) float32 matrix (leading dimensions in elements);
+ * kind 1 = host -> device, 2 = device -> host.  Packs one scan's (3,n) / (C,n) host matrix into its column
+ * range of a batch's device matrix (see "Ragged batch" below); the host side should be pinned. */
+int efgh_copy_matrix_async(void *dst, int64_t dst_ld, const void *src, int64_t src_ld, int64_t rows, int64_t cols,
+                           int kind, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Lattice build.  Together efgh_lattice_points + efgh_lattice_vertices replace one iteration of the
  * loop in GenerateData.__call__ (reference nets/generate_data.py:128-184): get_keys_and_barycentric
@@ -103,6 +109,34 @@ int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_o
                           int64_t *blur_neighbors, int32_t *blur_neighbors32, int64_t nbr_ld,
                           float *next_pts, int64_t next_ld, float next_divisor,
                           efgh_lattice_state *state, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Ragged batch: B scans per launch sequence (the reference is batch-size-1 only,
+ * nets/enet.py:107, nets/bilateralNN.py:162-165).  The point streams of the scans are concatenated: scan b owns
+ * points [scan_start[b], scan_start[b+1]) of `pts` / `barycentric` / `el_minus_gr` / `lattice_offset`.  Every scan
+ * keeps its own hash table, key box and insertion order, so per scan the outputs equal the single-scan calls';
+ * only the vertex numbering is global: scan b's vertices are [vertex_start[b], vertex_start[b+1]), and
+ * lattice_offset / blur_neighbors hold global vertex indices (local index + vertex_start[b]; -1 stays -1).
+ * The BCL entry points below then treat the whole batch as one lattice, unchanged.
+ *   scan_start: (B+1) int32 ON THE DEVICE, ascending, scan_start[0] = 0, no empty scan; for level l+1 pass
+ *     level l's vertex_start (= the first B+1 words of its batch_info);
+ *   n_cap_scan: capacity (points) of ONE scan - sizes each scan's hash table; n_cap_total: capacity of the
+ *     concatenated arrays (the true total is read from scan_start[B]);
+ *   batch_info: efgh_lattice_batch_info_ints(B) int32 on the device, written by efgh_lattice_points_batch
+ *     (words [0, B] = vertex_start) and read by efgh_lattice_vertices_batch;
+ *   state: totals over the batch (n, hash_cnt, status); its key box is unused. 1 <= B <= 64. */
+size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, int64_t n_cap_total);
+int64_t efgh_lattice_batch_info_ints(int B);
+int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start, int B,
+                              int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr, int64_t out_ld,
+                              int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info, void *workspace,
+                              size_t workspace_bytes, void *stream);
+int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t n_cap_scan,
+                                int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
+                                const int32_t *filter_offsets, int F, int64_t h,
+                                int64_t *blur_neighbors, int32_t *blur_neighbors32, int64_t nbr_ld,
+                                float *next_pts, int64_t next_ld, float next_divisor,
+                                efgh_lattice_state *state, int32_t *batch_info, void *workspace, size_t workspace_bytes,
+                                void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bilateral convolution layer pieces (reference nets/bilateralNN.py:148-263).  Lattice-side feature

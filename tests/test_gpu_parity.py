@@ -208,6 +208,82 @@ def test_scan_pipeline_vs_oracle(sensor, factor, dev):
         gpu_prev = got_l.double()
 
 
+@pytest.mark.parametrize("sizes", [None, (16384, 5000, 1, 12001)])
+def test_batched_pipeline_matches_single_scans(sizes, dev):
+    """Ragged batch: B scans through one launch sequence.  Per scan the lattice must equal the C oracle
+    bit for bit (own hash table / key box / insertion order, local vertex numbering), and the BCL outputs must
+    match the float64 oracle within the per-layer tolerance - i.e. batching changes nothing but the launch count."""
+    from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+    from oracle import lattice as ol, bcl as obcl
+    B = 4 if sizes else 3
+    n = 16384
+    sizes = list(sizes) if sizes else [n] * B
+    clouds = [synth.synth_scan(30 + b, "os1-64-16k")[:, :sizes[b]] for b in range(B)]
+    weights = make_enet_weights(synth.ENET_BCL, seed=3)
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=B)
+    if sizes != [n] * B:
+        pipe.set_scan_sizes(sizes)
+    g = torch.Generator().manual_seed(2)
+    feats = [torch.randn(32, sizes[b], generator=g) for b in range(B)]
+    pc_all = torch.zeros(3, B * n)
+    ft_all = torch.zeros(32, B * n)
+    o = 0
+    for b in range(B):
+        pc_all[:, o:o + sizes[b]] = torch.from_numpy(clouds[b])
+        ft_all[:, o:o + sizes[b]] = feats[b]
+        o += sizes[b]
+    for _ in range(2):                                  # twice: buffers are reused
+        pipe.enqueue(pc_all.to(dev), ft_all.to(dev))
+    tot = pipe.counts()
+    vs = pipe.vertex_starts()
+    for b in range(B):
+        want = ol.generate(clouds[b], synth.SCALE_MAP)
+        got = _to_np(pipe.level_dicts(scan=b))
+        for li, (gl, wl) in enumerate(zip(got, want)):
+            H.assert_level_equal(gl, wl, "batch scan %d L%d" % (b, li))
+        outs = pipe.outputs(scan=b)
+        prev = feats[b][None].double()
+        for li, w in enumerate(want):
+            args = (torch.from_numpy(w["pc1_barycentric"]), torch.from_numpy(w["pc1_lattice_offset"]),
+                    torch.from_numpy(w["pc1_blur_neighbors"]), weights[li])
+            ref = obcl.bcl_forward(torch.cat((torch.from_numpy(w["pc1_el_minus_gr"]).double(), prev), 1), *args, dtype=torch.float64)
+            got_l = outs[li].cpu()
+            assert tuple(got_l.shape) == tuple(ref.shape)
+            e = H.rel_err(got_l.numpy(), ref.numpy())
+            assert e < PER_LAYER_TOL, "batch scan %d level %d rel err %g" % (b, li, e)
+            prev = got_l.double()
+    for li in range(len(tot)):
+        assert vs[li][0] == 0 and vs[li][-1] == tot[li] and all(a < c for a, c in zip(vs[li], vs[li][1:]))
+
+
+def test_batched_forward_host_matches_enqueue(dev):
+    """The end-to-end entry point bench.py's e2e leg uses (pinned per-scan host buffers -> strided H2D -> batch ->
+    D2H of result rows, level records and per-scan vertex boundaries) returns what the device-resident path does."""
+    from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+    B, n = 3, 16384
+    clouds = [torch.from_numpy(synth.synth_scan(40 + b, "os1-64-16k")) for b in range(B)]
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.randn(32, n, generator=g) for _ in range(B)]
+    weights = make_enet_weights(synth.ENET_BCL, seed=3)
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=B)
+    pipe.enqueue(torch.cat(clouds, 1).to(dev), torch.cat(feats, 1).to(dev))
+    tot = pipe.counts()
+    want_vs = pipe.vertex_starts()
+    want_Z = pipe.levels[-1]["Z"][:tot[-1]].cpu()
+    out = torch.empty((tot[-1], 256)).pin_memory()
+    st = torch.empty((5, 24), dtype=torch.int32).pin_memory()
+    vs = torch.empty((5, B + 1), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.Stream(dev)
+    for use_graph in (False, True):
+        out.zero_()
+        pipe.forward_host([c.pin_memory() for c in clouds], [f.pin_memory() for f in feats], out, st, stream=stream,
+                          use_graph=use_graph, starts_host=vs)
+        stream.synchronize()
+        assert [int(v) for v in st[:, 1]] == tot
+        assert vs.tolist() == want_vs
+        assert H.rel_err(out.numpy(), want_Z.numpy()) < 1e-6          # same kernels; only the atomics' order differs
+
+
 # ------------------------------------------------------------------------------------------------
 # wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
 # ------------------------------------------------------------------------------------------------

@@ -37,12 +37,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
-    ap.add_argument("--streams", type=int, default=4, help="concurrent scan pipelines per GPU")
-    ap.add_argument("--scan-batch", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=2, help="concurrent scan pipelines per GPU")
+    ap.add_argument("--scan-batch", type=int, default=8,
                     help="scans per launch sequence (ragged batched lattices, SURVEY §8 f2); 1 = one launch sequence per scan")
     ap.add_argument("--sensor", default=SENSOR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage timing table to stderr")
+    ap.add_argument("--atomic-splat", action="store_true", help="splat with vector atomics instead of the gather-form splat")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -201,8 +202,9 @@ def run_ours(args):
     # resident inputs, one (3, G*N) / (32, G*N) pair per group: scan b of the group in columns [b*N, (b+1)*N)
     pc_dev = [torch.from_numpy(np.concatenate(clouds[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
     ft_dev = [torch.from_numpy(np.concatenate(feats[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
-    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G) for _ in range(P)]
-    pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0)
+    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G, gather_splat=not args.atomic_splat) for _ in range(P)]
+    pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0,
+                                                 gather_splat=not args.atomic_splat)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
     main = torch.cuda.current_stream(dev)
 
@@ -358,6 +360,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd" % (args.sensor, N),
                    "scans_per_gpu_per_step": B, "scans_per_launch_sequence": G, "concurrent_pipelines": P, "levels_H": counts_scan0,
                    "l2_policy": "inputs larger than L2 (%d scans x %.1f MB resident, cycled)" % (B, (clouds[0].nbytes + feats[0].nbytes) / 1e6),
+                   "splat": "gather (vertex -> contributions lists)" if pipes[0].gather_splat else "atomic scatter",
                    "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                    "algorithmic_MB_per_scan": total_bytes / 1e6,
                    "scan_roofline_frac": total_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},

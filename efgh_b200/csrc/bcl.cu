@@ -92,6 +92,154 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const 
   }
 }
 
+// ---- gather-form splat ---------------------------------------------------------------------------------------------
+// The atomic splat above is bound by the L2's atomic units (~150 G red.v4/s measured) and every lattice vertex
+// receives 5 - 20 contributions.  With the vertex -> contributions lists the lattice build can emit
+// (efgh_lattice_*_batch: vertex_offsets / contributions / point_rows) the same sums are formed in registers: one warp
+// per vertex, LPR lanes x float4 span the previous level's point-major row, 32 / LPR contributions are processed
+// side by side, the partial sums meet through shuffles, and the row is written ONCE - already multiplied by the
+// density normalisation 1 / (sum of weights + 1e-5) (reference nets/bilateralNN.py:193-211).  That replaces the
+// zero-fill of S, the atomics and the normalisation pass.  The level's own 4 el_minus_gr channels and the 4
+// barycentric weights of a point come from ONE 32-byte sector (point_rows).  Vertices with more than kHeavy
+// contributions (coincident points) are listed by the lattice build and get a whole CTA.
+constexpr int kSplatHeavy = 128;      // == lattice.cu kHeavy
+constexpr int kSplatMaxHeavy = 1024;  // == lattice.cu kMaxHeavy
+
+template <int NV, int LPR>
+struct SplatAcc {
+  float4 acc[NV];
+  float acc1, wacc;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc1 = 0.f; wacc = 0.f;
+  }
+  // contributions [base, min(base + 32, e1)) of one vertex
+  __device__ __forceinline__ void batch(const float *__restrict__ point_rows, const float *__restrict__ feat2, int64_t sn2, int C24,
+                                        const int32_t *__restrict__ contrib, int base, int e1, int lane) {
+    constexpr int G = 32 / LPR;
+    const int g = lane / LPR, l = lane - g * LPR;
+    const int mine = base + lane < e1 ? __ldg(contrib + base + lane) : 0;      // 32 list entries per coalesced load
+    const float wmine = base + lane < e1 ? __ldg(point_rows + (int64_t)(mine >> 2) * 8 + 4 + (mine & 3)) : 0.f;
+    const int cnt = min(32, e1 - base);
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += G) {                                      // warp-uniform; fully unrolled: the loads of all
+      if (j0 >= cnt) break;                                                    // iterations are independent and issue back to back
+      const int j = j0 + g;
+      const int p = __shfl_sync(0xffffffffu, mine, j & 31);
+      const float wt = __shfl_sync(0xffffffffu, wmine, j & 31);              // 0 beyond the list: contributes nothing
+      const int i = p >> 2;
+      if (l < 4) acc1 = fmaf(wt, __ldg(point_rows + (int64_t)i * 8 + l), acc1);
+      if (l == 0) wacc += wt;
+      const float4 *row = reinterpret_cast<const float4 *>(feat2 + (int64_t)i * sn2);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c4 = l + k * LPR;
+        if (c4 < C24) {
+          const float4 x = __ldg(row + c4);
+          acc[k].x = fmaf(wt, x.x, acc[k].x); acc[k].y = fmaf(wt, x.y, acc[k].y);
+          acc[k].z = fmaf(wt, x.z, acc[k].z); acc[k].w = fmaf(wt, x.w, acc[k].w);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void combine_groups() {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+      wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+      }
+    }
+  }
+  // lanes of group 0 write the row (wacc valid on lane 0)
+  __device__ __forceinline__ void store(float *__restrict__ S, int64_t ldS, int v, int C24, int normalize, float *inv_out, int lane) {
+    const float wsum = __shfl_sync(0xffffffffu, wacc, 0);
+    const float inv = __fdiv_rn(1.0f, __fadd_rn(wsum, 1e-5f));
+    const float scl = normalize ? inv : 1.0f;
+    if (lane < LPR) {
+      float *out = S + (int64_t)(v + 1) * ldS;
+      if (lane < 4) out[lane] = acc1 * scl;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c4 = lane + k * LPR;
+        if (c4 < C24) {
+          float4 o4 = acc[k];
+          o4.x *= scl; o4.y *= scl; o4.z *= scl; o4.w *= scl;
+          *reinterpret_cast<float4 *>(out + 4 + 4 * c4) = o4;
+        }
+      }
+      if (inv_out && lane == 0) inv_out[v + 1] = inv;
+    }
+  }
+};
+
+template <int NV, int LPR>
+__global__ void __launch_bounds__(256)
+k_splat_gather(const float *__restrict__ point_rows, const float *__restrict__ feat2, int64_t sn2, int C2,
+               const int32_t *__restrict__ voff, const int32_t *__restrict__ contrib, int rows_host,
+               const int32_t *rows_dev, int normalize, float *__restrict__ S, int64_t ldS, float *__restrict__ inv_out) {
+  const int H = rows_dev ? min(*rows_dev, rows_host) : rows_host;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int C = 4 + C2, C24 = C2 >> 2;
+  if (blockIdx.x == 0 && threadIdx.x < C) S[threadIdx.x] = 0.f;                 // sink row ("-1 neighbour")
+  if (blockIdx.x == 0 && threadIdx.x == 0 && inv_out) inv_out[0] = __fdiv_rn(1.0f, 1e-5f);
+  SplatAcc<NV, LPR> A;
+
+  // heavy vertices: the 8 warps of a CTA share one vertex's list, partial sums meet in shared memory
+  const int n_heavy = voff[rows_host + 1];
+  const bool listed = n_heavy <= kSplatMaxHeavy;          // (an overflowing list is ignored: the warps below take all)
+  if (listed && n_heavy > 0) {
+    __shared__ float s_part[8][4 * NV * LPR + 8];
+    for (int hi = blockIdx.x; hi < n_heavy; hi += gridDim.x) {
+      const int v = voff[rows_host + 2 + hi];
+      if (v >= H) continue;
+      const int e0 = __ldg(voff + v), e1 = __ldg(voff + v + 1);
+      A.clear();
+      for (int base = e0 + 32 * wid; base < e1; base += 32 * 8) A.batch(point_rows, feat2, sn2, C24, contrib, base, e1, lane);
+      A.combine_groups();
+      if (lane < LPR) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) *reinterpret_cast<float4 *>(&s_part[wid][4 * (lane + k * LPR)]) = A.acc[k];
+        if (lane < 4) s_part[wid][4 * NV * LPR + lane] = A.acc1;
+        if (lane == 0) s_part[wid][4 * NV * LPR + 4] = A.wacc;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        if (lane < LPR) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w8 = 0; w8 < 8; ++w8) {
+              const float4 q = *reinterpret_cast<const float4 *>(&s_part[w8][4 * (lane + k * LPR)]);
+              t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+            }
+            A.acc[k] = t;
+          }
+          float t1 = 0.f, tw = 0.f;
+          for (int w8 = 0; w8 < 8; ++w8) { t1 += s_part[w8][4 * NV * LPR + (lane & 3)]; tw += s_part[w8][4 * NV * LPR + 4]; }
+          A.acc1 = t1; A.wacc = tw;
+        }
+        A.store(S, ldS, v, C24, normalize, inv_out, lane);
+      }
+      __syncthreads();
+    }
+  }
+
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < H; v += warps) {
+    const int e0 = __ldg(voff + v), e1 = __ldg(voff + v + 1);
+    if (listed && e1 - e0 > kSplatHeavy) continue;        // done above
+    A.clear();
+    for (int base = e0; base < e1; base += 32) A.batch(point_rows, feat2, sn2, C24, contrib, base, e1, lane);
+    A.combine_groups();
+    A.store(S, ldS, v, C24, normalize, inv_out, lane);
+  }
+}
+
 __device__ __forceinline__ void zero_rows(float *__restrict__ M, int64_t ld, int C, int rows, int64_t tid, int64_t stride) {
   if (ld == C && C % 4 == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0) {
     float4 *M4 = reinterpret_cast<float4 *>(M);
@@ -568,6 +716,32 @@ extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t str
     };
     return wide ? launch(k_scatter<IdxT, 32>) : launch(k_scatter<IdxT, 8>);
   });
+}
+
+extern "C" int efgh_bcl_splat_gather(const float *point_rows, const float *feat2, int64_t stride_n2, int C2,
+                                     const int32_t *vertex_offsets, const int32_t *contributions, int64_t rows,
+                                     const int32_t *rows_dev, int normalize, float *S, int64_t ldS, float *inv_out,
+                                     void *stream) {
+  EFGH_REQUIRE(C2 > 0 && C2 % 4 == 0 && C2 <= 512, "efgh_bcl_splat_gather: C2=%d must be a multiple of 4, at most 512", C2);
+  EFGH_REQUIRE(rows >= 0 && rows < (1ll << 30), "efgh_bcl_splat_gather: bad rows");
+  EFGH_REQUIRE(point_rows && feat2 && vertex_offsets && contributions && S, "efgh_bcl_splat_gather: null pointer");
+  EFGH_REQUIRE(stride_n2 % 4 == 0 && ldS % 4 == 0 && ldS >= 4 + C2 && (reinterpret_cast<uintptr_t>(feat2) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(point_rows) & 15) == 0,
+               "efgh_bcl_splat_gather: point_rows / feat2 / S rows must be 16-byte aligned (strides multiples of 4)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for((rows + 1) * 32, 256, 8);
+  const int c24 = C2 / 4;
+#define EFGH_SPLAT(NV, LPR)                                                                                              \
+  k_splat_gather<NV, LPR><<<grid, 256, 0, s>>>(point_rows, feat2, stride_n2, C2, vertex_offsets, contributions, (int)rows, \
+                                               rows_dev, normalize, S, ldS, inv_out)
+  if (c24 <= 8) EFGH_SPLAT(1, 8);
+  else if (c24 <= 16) EFGH_SPLAT(1, 16);
+  else if (c24 <= 32) EFGH_SPLAT(1, 32);
+  else if (c24 <= 64) EFGH_SPLAT(2, 32);
+  else EFGH_SPLAT(4, 32);
+#undef EFGH_SPLAT
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
 }
 
 extern "C" int efgh_bcl_zero(float *S, int64_t ldS, int C, float *wsum, float *Y2, int64_t ldY2, int C2, int64_t rows,

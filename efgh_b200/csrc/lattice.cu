@@ -57,7 +57,18 @@ struct Batch {
   int32_t *info;
   int B, tm_off, box_off;
   long long tstride;
+  // optional vertex -> contributions lists (CSR) for the gather-form splat: voff[h] .. voff[h+1] index `contrib`,
+  // whose entries are stream positions 4 * point + remainder
+  int32_t *voff;             // [0, h_cap]: offsets; [h_cap + 1]: number of heavy vertices; then their indices
+  int32_t *contrib;
+  int32_t *cursor;           // workspace, h_cap ints
+  float *point_rows;         // optional (n, 8) point-major copy: el_minus_gr[0..3], barycentric[0..3]
+  int h_cap;
 };
+// A vertex with more than kHeavy contributions (coincident points, e.g. returns clipped to the range box) is listed so
+// that the gather-form splat can put a whole CTA on it instead of one warp.
+constexpr int kHeavy = 128;
+constexpr int kMaxHeavy = 1024;
 inline int batch_tm_off(int B) { return (B + 1 + 7) & ~7; }
 inline int batch_box_off(int B) { return batch_tm_off(B) + ((B + 7) & ~7); }
 
@@ -76,6 +87,7 @@ struct Workspace {
   int4 *slots;
   unsigned long long *vkeys;
   unsigned long long *tiles;
+  int32_t *cursor;
   int64_t table_cap;
   size_t bytes;
 };
@@ -100,6 +112,7 @@ Workspace carve(void *base, int64_t n_cap, int B = 1, int64_t n_cap_scan = -1) {
   w.slots = reinterpret_cast<int4 *>(b + off); off = align_up(off + sizeof(int4) * n_cap);
   w.vkeys = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * 4 * n_cap);
   w.tiles = reinterpret_cast<unsigned long long *>(b + off); off = align_up(off + sizeof(unsigned long long) * ((n_cap + kTile - 1) / kTile + 1));
+  w.cursor = reinterpret_cast<int32_t *>(b + off); off = align_up(off + sizeof(int32_t) * 4 * n_cap);
   w.bytes = off;
   return w;
 }
@@ -155,6 +168,7 @@ __global__ void k_clear(efgh_lattice_state *st, const int32_t *n_dev, int n_host
   int n_tiles = (n + kTile - 1) / kTile;
   for (int64_t i = tid; i < n_tiles && i < n_tiles_cap; i += stride) tiles[i] = 0ull;
   if (tid == 0) {
+    if (bt.voff) bt.voff[bt.h_cap + 1] = 0;
     st->n = n;
     st->hash_cnt = 0;
     st->status = 0;
@@ -266,6 +280,11 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
       bary[c * out_ld + i] = b[c];
       elmgr[c * out_ld + i] = diff[c];
     }
+    if (bt.point_rows) {
+      float4 *pr = reinterpret_cast<float4 *>(bt.point_rows + (int64_t)i * 8);
+      pr[0] = make_float4(diff[0], diff[1], diff[2], diff[3]);
+      pr[1] = make_float4(b[0], b[1], b[2], b[3]);
+    }
 
     int s4[4];
     unsigned long long key4[4], cur4[4];
@@ -300,6 +319,7 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
         if (cur == kEmpty) cur = atomicCAS(&table[h].key, kEmpty, key);
       }
       atomicMin(&table[h].first_pos, 4 * i + r);
+      if (bt.voff) atomicAdd(&table[h].index, 1);              // index = (number of contributions) - 1 until k_assign
       s4[r] = (int)(slot_base + h);
     }
     slots[i] = make_int4(s4[0], s4[1], s4[2], s4[3]);
@@ -372,8 +392,9 @@ constexpr int kAssignThreads = kTile / 2;
 __global__ void __launch_bounds__(kAssignThreads)
 k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
          unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap, Batch bt) {
-  __shared__ int s_tile, s_prefix;
-  __shared__ int s_warp[kAssignThreads / 32];
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned long long s_warp[kAssignThreads / 32];
   const int n = st->n;
   const int n_tiles = (n + kTile - 1) / kTile;
   if (threadIdx.x == 0) s_tile = atomicAdd(&st->tile_counter, 1);
@@ -391,7 +412,8 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
     sl[4 * q] = s.x; sl[4 * q + 1] = s.y; sl[4 * q + 2] = s.z; sl[4 * q + 3] = s.w;
   }
   unsigned long long kk[8];
-  int cnt = 0;
+  int cc[8];                                                   // contributions of the key (valid for first occurrences)
+  int cnt = 0, ccnt = 0;
   {
     int4 ent[8];
 #pragma unroll
@@ -401,39 +423,44 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
     for (int e = 0; e < 8; ++e) {
       fl[e] = ent[e].z == 4 * (i0 + (e >> 2)) + (e & 3);                           // first_pos == own stream position
       cnt += fl[e];
+      cc[e] = ent[e].w + 1;
+      ccnt += fl[e] ? cc[e] : 0;
       kk[e] = ((unsigned long long)(unsigned)ent[e].y << 32) | (unsigned)ent[e].x;
     }
   }
 
-  // block exclusive scan of cnt
+  // block exclusive scan of (cnt, ccnt), packed low / high 32 bits
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = cnt;
+  const unsigned long long mine = (unsigned long long)(unsigned)cnt | ((unsigned long long)(unsigned)ccnt << 32);
+  unsigned long long inc = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    int v = lane < kAssignThreads / 32 ? s_warp[lane] : 0;
+    unsigned long long v = lane < kAssignThreads / 32 ? s_warp[lane] : 0ull;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, v, o);
+      unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
       if (lane >= o) v += t;
     }
     if (lane < kAssignThreads / 32) s_warp[lane] = v;  // inclusive warp totals
   }
   __syncthreads();
-  const int block_total = s_warp[kAssignThreads / 32 - 1];
-  const int local = inc - cnt + (wid ? s_warp[wid - 1] : 0);
+  const unsigned long long block_total = s_warp[kAssignThreads / 32 - 1];
+  const unsigned long long local = inc - mine + (wid ? s_warp[wid - 1] : 0ull);
+  // look-back word: bits 63..62 state, bits 59..30 contributions, bits 29..0 vertices (both < 2^30)
+  const unsigned long long block_word = (block_total & 0x3fffffffull) | ((block_total >> 32) << 30);
 
   if (wid == 0) {
     // warp-parallel look-back: lane l inspects tile (base - l); stop at the first inclusive prefix
     volatile unsigned long long *vt = tiles;
-    int prefix = 0;
+    unsigned long long prefix = 0;
     if (tile > 0) {
-      if (lane == 0) vt[tile] = (1ull << 62) | (unsigned)block_total;
+      if (lane == 0) vt[tile] = (1ull << 62) | block_word;
       int base = tile - 1;
       while (true) {
         const int j = base - lane;
@@ -441,28 +468,31 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
         if (j >= 0) { do { w = vt[j]; } while ((w >> 62) == 0); }
         const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
         const int first = __ffs(incl) - 1;                  // nearest tile that already knows its inclusive prefix
-        int contrib = (first < 0 || lane <= first) ? (int)(unsigned)(w & 0xffffffffu) : 0;
+        unsigned long long contrib = (first < 0 || lane <= first) ? (w & 0x0fffffffffffffffull) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        prefix += contrib;
+        prefix += contrib;                                  // the two 30-bit fields cannot carry into each other
         if (first >= 0) break;
         base -= 32;
       }
     }
     if (lane == 0) {
       __threadfence();
-      vt[tile] = (2ull << 62) | (unsigned)(prefix + block_total);
+      vt[tile] = (2ull << 62) | (prefix + block_word);
       s_prefix = prefix;
       if (tile == n_tiles - 1) {
-        const int total = prefix + block_total;
+        const unsigned long long tw = prefix + block_word;
+        const int total = (int)(tw & 0x3fffffffull);
         st->hash_cnt = total;
         if (bt.pt_start) bt.info[bt.B] = total;             // vertex_start[B]
+        if (bt.voff && total <= h_cap) bt.voff[total] = (int)(tw >> 30);
         if (total > h_cap) atomicOr(&st->status, EFGH_ST_VERTEX_CAP);
       }
     }
   }
   __syncthreads();
-  int idx = s_prefix + local;
+  int idx = (int)(s_prefix & 0x3fffffffull) + (int)(unsigned)(local & 0xffffffffull);
+  int coff = (int)(s_prefix >> 30) + (int)(local >> 32);
   if (bt.pt_start) {
     // vertex_start[b] = number of vertices created before scan b's first point (scans are never empty)
     const int c0 = fl[0] + fl[1] + fl[2] + fl[3];
@@ -474,7 +504,20 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e)
-    if (fl[e]) { table[sl[e]].index = idx; vkeys[idx] = kk[e]; ++idx; }
+    if (fl[e]) {
+      table[sl[e]].index = idx;
+      if (idx < h_cap) {
+        vkeys[idx] = kk[e];
+        if (bt.voff) {
+          bt.voff[idx] = coff; bt.cursor[idx] = coff; coff += cc[e];
+          if (cc[e] > kHeavy) {
+            const int slot = atomicAdd(&bt.voff[bt.h_cap + 1], 1);
+            if (slot < kMaxHeavy) bt.voff[bt.h_cap + 2 + slot] = idx;
+          }
+        }
+      }
+      ++idx;
+    }
 }
 
 __device__ __forceinline__ int table_find(const Entry *__restrict__ table, unsigned mask, unsigned long long key) {
@@ -524,6 +567,14 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
       }
       if (loff32) {
         loff32[i] = v0; loff32[off_ld + i] = v1; loff32[2 * off_ld + i] = v2; loff32[3 * off_ld + i] = v3;
+      }
+      if (bt.contrib) {                                      // vertex -> contributions lists (order within a vertex is arbitrary)
+        const int v[4] = {v0, v1, v2, v3};
+        int pos[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) pos[r] = v[r] < h_cap ? atomicAdd(&bt.cursor[v[r]], 1) : -1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (pos[r] >= 0) bt.contrib[pos[r]] = 4 * i + r;
       }
     }
   }
@@ -644,6 +695,8 @@ extern "C" size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, 
   return carve(nullptr, n_cap_total, B, n_cap_scan).bytes;
 }
 
+extern "C" int64_t efgh_lattice_vertex_offsets_ints(int64_t h_cap) { return h_cap + 2 + kMaxHeavy; }
+
 extern "C" int64_t efgh_lattice_batch_info_ints(int B) { return B < 1 ? 0 : (int64_t)batch_box_off(B) + 8 * (int64_t)B; }
 
 namespace {
@@ -662,6 +715,7 @@ int lattice_points_impl(const char *who, const float *pts, int64_t pts_ld, int64
   }
   EFGH_REQUIRE(w.table_cap * B < (1ll << 31), "%s: hash tables of the batch exceed 2^31 entries", who);
   bt.tstride = w.table_cap;
+  bt.cursor = w.cursor;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n_tiles_cap = (int)((n + kTile - 1) / kTile) + 1;
   k_clear<<<grid_for(w.table_cap, 256, 8), 256, 0, s>>>(state, n_dev, (int)n, w.table_cap, w.table, w.tiles, n_tiles_cap, bt);
@@ -694,6 +748,7 @@ int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, i
     return EFGH_ENOMEM;
   }
   bt.tstride = w.table_cap;
+  bt.cursor = w.cursor;
   if (n == 0) return EFGH_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t vitems = h * (F > 0 ? 4 : 1);
@@ -706,11 +761,15 @@ int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, i
   return EFGH_OK;
 }
 
-int make_batch(const char *who, const int32_t *scan_start, int B, int64_t n_cap_scan, int32_t *batch_info, Batch *bt) {
+int make_batch(const char *who, const int32_t *scan_start, int B, int64_t n_cap_scan, int32_t *batch_info, Batch *bt,
+               int32_t *voff, int32_t *contrib, float *point_rows, int64_t h_cap) {
   EFGH_REQUIRE(B >= 1 && B <= kMaxBatch, "%s: batch of %d scans (1..%d supported)", who, B, kMaxBatch);
   EFGH_REQUIRE(scan_start && batch_info && n_cap_scan >= 1, "%s: null scan_start / batch_info or n_cap_scan < 1", who);
   bt->pt_start = scan_start; bt->info = batch_info; bt->B = B;
   bt->tm_off = batch_tm_off(B); bt->box_off = batch_box_off(B); bt->tstride = 0;
+  bt->voff = voff; bt->contrib = contrib; bt->cursor = nullptr; bt->point_rows = point_rows;
+  bt->h_cap = (int)(h_cap < (1ll << 30) ? h_cap : (1ll << 30));
+  EFGH_REQUIRE(!point_rows || (reinterpret_cast<uintptr_t>(point_rows) & 15) == 0, "%s: point_rows must be 16-byte aligned", who);
   return EFGH_OK;
 }
 
@@ -720,7 +779,7 @@ extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, 
                                    float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap,
                                    efgh_lattice_state *state, void *workspace, size_t workspace_bytes,
                                    void *stream) {
-  Batch bt = {nullptr, nullptr, 1, 0, 0, 0};
+  Batch bt = {nullptr, nullptr, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
   return lattice_points_impl("efgh_lattice_points", pts, pts_ld, n, n_dev, scale, barycentric, el_minus_gr, out_ld, h_cap,
                              state, workspace, workspace_bytes, stream, bt, n);
 }
@@ -730,7 +789,7 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
                                      int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
                                      float next_divisor, efgh_lattice_state *state, void *workspace,
                                      size_t workspace_bytes, void *stream) {
-  Batch bt = {nullptr, nullptr, 1, 0, 0, 0};
+  Batch bt = {nullptr, nullptr, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
   return lattice_vertices_impl("efgh_lattice_vertices", n, lattice_offset, lattice_offset32, off_ld, filter_offsets, F, h,
                                blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld, next_divisor, state, workspace,
                                workspace_bytes, stream, bt, n);
@@ -739,9 +798,12 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
 extern "C" int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start,
                                          int B, int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr,
                                          int64_t out_ld, int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info,
-                                         void *workspace, size_t workspace_bytes, void *stream) {
+                                         int32_t *vertex_offsets, float *point_rows, void *workspace, size_t workspace_bytes,
+                                         void *stream) {
   Batch bt;
-  if (int rc = make_batch("efgh_lattice_points_batch", scan_start, B, n_cap_scan, batch_info, &bt)) return rc;
+  if (int rc = make_batch("efgh_lattice_points_batch", scan_start, B, n_cap_scan, batch_info, &bt, vertex_offsets, nullptr,
+                          point_rows, h_cap))
+    return rc;
   return lattice_points_impl("efgh_lattice_points_batch", pts, pts_ld, n_cap_total, nullptr, scale, barycentric,
                              el_minus_gr, out_ld, h_cap, state, workspace, workspace_bytes, stream, bt, n_cap_scan);
 }
@@ -751,9 +813,11 @@ extern "C" int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *s
                                            const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
                                            int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
                                            float next_divisor, efgh_lattice_state *state, int32_t *batch_info,
-                                           void *workspace, size_t workspace_bytes, void *stream) {
+                                           int32_t *contributions, void *workspace, size_t workspace_bytes, void *stream) {
   Batch bt;
-  if (int rc = make_batch("efgh_lattice_vertices_batch", scan_start, B, n_cap_scan, batch_info, &bt)) return rc;
+  if (int rc = make_batch("efgh_lattice_vertices_batch", scan_start, B, n_cap_scan, batch_info, &bt, nullptr, contributions,
+                          nullptr, h))
+    return rc;
   return lattice_vertices_impl("efgh_lattice_vertices_batch", n_cap_total, lattice_offset, lattice_offset32, off_ld,
                                filter_offsets, F, h, blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
                                next_divisor, state, workspace, workspace_bytes, stream, bt, n_cap_scan);

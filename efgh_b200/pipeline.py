@@ -34,17 +34,22 @@ _ACT = {"none": 0, "relu": 1, "leaky": 2}
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
                  vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
-                 precision="3xtf32", batch=1):
+                 precision="3xtf32", batch=1, gather_splat=True):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
         vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
         precision: "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05, one pass) or "fp32" (CUDA cores);
+        gather_splat: levels >= 1 (whose input features are the previous level's point-major output rows) splat
+        through the vertex -> contributions lists of the lattice build - no atomics, zero-fill and normalisation
+        fused.  Level 0 (channel-major (C, N) input, working set beyond the L2 in batch mode) keeps the atomic scatter;
         batch: scans per launch sequence, each of n_points points (inputs are then (3, batch*n_points) /
         (C, batch*n_points), scan b in columns [b*n_points, (b+1)*n_points))."""
         self.dev = torch.device(device)
         self.L = _capi.lib()
         self.B = int(batch)
         assert 1 <= self.B <= 64
+        self.gather_splat = bool(gather_splat)
+        self.batch_api = self.B > 1 or self.gather_splat       # the batch entry points also serve a batch of one
         self.n_scan = int(n_points)
         self.n0 = int(n_points) * self.B
         self.smap = scales_filter_map
@@ -80,6 +85,10 @@ class ScanPipeline(object):
                 lv = {
                     "n_cap_scan": n_cap_scan,
                     "info": torch.zeros(max(int(self.L.efgh_lattice_batch_info_ints(self.B)), 1), dtype=i32, device=dev),
+                    "gs": self.gather_splat and li > 0,
+                    "voff": torch.zeros(int(self.L.efgh_lattice_vertex_offsets_ints(h_cap)), dtype=i32, device=dev) if self.gather_splat and li > 0 else None,
+                    "prow": torch.zeros((n_cap, 8), dtype=f32, device=dev) if self.gather_splat and li > 0 else None,
+                    "contrib": torch.zeros(4 * n_cap, dtype=i32, device=dev) if self.gather_splat and li > 0 else None,
                     "n_cap": n_cap, "h_cap": h_cap, "F": F, "scale": float(scale), "cin": cin, "cmid": cmid, "cout": cout,
                     "divisor": float(np.float32(self.gd.expected_std * scale)),
                     "offs": torch.from_numpy(self.gd.radius2offset[radius].astype(np.int32)).to(dev),
@@ -112,7 +121,7 @@ class ScanPipeline(object):
                                                                  torch.cuda.current_stream(dev).cuda_stream), "efgh_bcl_pack_weights")
                         lv[nm] = img
                     lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin) > 1
-                if self.B > 1:
+                if self.batch_api:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, n_cap_scan, n_cap))
                 else:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
@@ -125,7 +134,8 @@ class ScanPipeline(object):
             self.scan_start = torch.tensor(self._starts0, dtype=i32, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
-        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 1 + 2)
+        # per launch sequence: clear/points/assign, vertices, zero, splat (+ normalise | level-0 transpose), conv1, conv2
+        self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 2) + sum(0 if lv["gs"] else 1 for lv in self.levels)
 
     def set_scan_sizes(self, sizes):
         """Batched pipelines: ragged batch - scan b has sizes[b] (1 <= sizes[b] <= n_points) points, stored back to
@@ -178,21 +188,23 @@ class ScanPipeline(object):
         prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
         n_dev = None
         seg = self.scan_start.data_ptr()                      # batched: point-stream boundaries of the level
-        if self.B > 1:
+        if self.batch_api:
             n_dev = seg + 4 * self.B                          # total points of a (possibly ragged) batch
         for li, lv in enumerate(self.levels):
             st = self.states[li].data_ptr()
             n_cap, h_cap, cin = lv["n_cap"], lv["h_cap"], lv["cin"]
             h_dev = st + 4           # &state.hash_cnt
-            if self.B > 1:
+            if self.batch_api:
                 info = lv["info"].data_ptr()
                 timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points_batch(
                     pts_ptr, pts_ld, n_cap, seg, self.B, lv["n_cap_scan"], lv["scale"], lv["bary"].data_ptr(),
-                    lv["elmgr"].data_ptr(), n_cap, h_cap, st, info, ws, wsn, s_lat), "efgh_lattice_points_batch"))
+                    lv["elmgr"].data_ptr(), n_cap, h_cap, st, info, _capi.ptr(lv["voff"]), _capi.ptr(lv["prow"]), ws, wsn, s_lat),
+                    "efgh_lattice_points_batch"))
                 timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices_batch(
                     n_cap, seg, self.B, lv["n_cap_scan"], _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap,
                     lv["offs"].data_ptr(), lv["F"], h_cap, _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap,
-                    _capi.ptr(lv["next"]), h_cap, lv["divisor"], st, info, ws, wsn, s_lat), "efgh_lattice_vertices_batch"))
+                    _capi.ptr(lv["next"]), h_cap, lv["divisor"], st, info, _capi.ptr(lv["contrib"]), ws, wsn, s_lat),
+                    "efgh_lattice_vertices_batch"))
                 seg = info                                    # vertex_start of this level = scan_start of the next
             else:
                 timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points(
@@ -205,7 +217,9 @@ class ScanPipeline(object):
             S = lv["S"].data_ptr()
             zero_y = lv["tc"] and lv["split0"]                # split-K accumulator of the tensor-core conv
             # zero-fill of this level's accumulators: on the lattice stream, i.e. off the BCL chain's critical path
-            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(S, cin, cin, lv["wsum"].data_ptr(), lv["Y"].data_ptr() if zero_y else None,
+            gs = lv["gs"]                                     # the gather-form splat writes every row of S itself
+            timed("L%d.zero" % li, lambda: ck(L.efgh_bcl_zero(None if gs else S, cin, cin, None if gs else lv["wsum"].data_ptr(),
+                                                              lv["Y"].data_ptr() if zero_y else None,
                                                               lv["cmid"], lv["cmid"], h_cap, h_dev, 1, s_lat), "efgh_bcl_zero"))
             if lat is not None:
                 ev = torch.cuda.Event()
@@ -213,6 +227,13 @@ class ScanPipeline(object):
                 main.wait_event(ev)                   # BCL of this level may start; the next level's lattice runs on
 
             def splat():
+                if gs:
+                    # [el_minus_gr (4 ch, channel-major) ; previous features (point-major rows)] summed per vertex in
+                    # registers through the lattice's vertex -> contributions lists, normalised, written once
+                    ck(L.efgh_bcl_splat_gather(lv["prow"].data_ptr(), prev_ptr, prev_sn, prev_c, lv["voff"].data_ptr(),
+                                               lv["contrib"].data_ptr(), h_cap, h_dev, 1 if self.use_norm else 0, S, cin,
+                                               None, s), "efgh_bcl_splat_gather")
+                    return
                 # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat
                 ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev,
                                       lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
@@ -306,7 +327,7 @@ class ScanPipeline(object):
 
     def vertex_starts(self):
         """Batched mode: per level, the (B+1) global vertex boundaries of the scans (synchronising read)."""
-        return [lv["info"][:self.B + 1].cpu().tolist() if self.B > 1 else [0, c]
+        return [lv["info"][:self.B + 1].cpu().tolist() if self.batch_api else [0, c]
                 for lv, c in zip(self.levels, self.counts())]
 
     def level_dicts(self, scan=None):

@@ -123,20 +123,28 @@ int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_o
  *     concatenated arrays (the true total is read from scan_start[B]);
  *   batch_info: efgh_lattice_batch_info_ints(B) int32 on the device, written by efgh_lattice_points_batch
  *     (words [0, B] = vertex_start) and read by efgh_lattice_vertices_batch;
- *   state: totals over the batch (n, hash_cnt, status); its key box is unused. 1 <= B <= 64. */
+ *   state: totals over the batch (n, hash_cnt, status); its key box is unused. 1 <= B <= 64;
+ *   vertex_offsets (efgh_lattice_vertex_offsets_ints(h_cap) int32) / contributions (4*n_cap_total int32), both
+ *     optional (NULL): the transposed view of lattice_offset as vertex -> contribution lists for the gather-form
+ *     splat (efgh_bcl_splat_gather): contributions[vertex_offsets[h] .. vertex_offsets[h+1]) are the stream
+ *     positions 4*point + remainder whose lattice_offset is h, in arbitrary order; behind the h_cap+1 offsets the
+ *     array carries the list of vertices with more than 128 contributions.  contributions needs lattice_offset or
+ *     lattice_offset32 to be requested too, and vertex_offsets to have been given to the points call of the level;
+ *   point_rows (n_cap_total, 8) f32, optional: point-major copy [el_minus_gr[0..3], barycentric[0..3]] per point. */
+int64_t efgh_lattice_vertex_offsets_ints(int64_t h_cap);
 size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, int64_t n_cap_total);
 int64_t efgh_lattice_batch_info_ints(int B);
 int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start, int B,
                               int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr, int64_t out_ld,
-                              int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info, void *workspace,
-                              size_t workspace_bytes, void *stream);
+                              int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info, int32_t *vertex_offsets,
+                              float *point_rows, void *workspace, size_t workspace_bytes, void *stream);
 int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t n_cap_scan,
                                 int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
                                 const int32_t *filter_offsets, int F, int64_t h,
                                 int64_t *blur_neighbors, int32_t *blur_neighbors32, int64_t nbr_ld,
                                 float *next_pts, int64_t next_ld, float next_divisor,
-                                efgh_lattice_state *state, int32_t *batch_info, void *workspace, size_t workspace_bytes,
-                                void *stream);
+                                efgh_lattice_state *state, int32_t *batch_info, int32_t *contributions, void *workspace,
+                                size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bilateral convolution layer pieces (reference nets/bilateralNN.py:148-263).  Lattice-side feature
@@ -145,6 +153,20 @@ int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, 
  * addressed as base[c*stride_c + n*stride_n] so both the reference's (C,N) layout and a point-major
  * layout work.  idx_bits is 64 (reference int64 tensors) or 32.
  * ---------------------------------------------------------------------------------------------- */
+
+/* Gather-form splat + density normalisation in one pass (reference nets/bilateralNN.py:176-211, with E-Net's input
+ * wiring `cat(el_minus_gr, previous features)`, reference nets/enet.py:113-137): for every vertex h
+ *   S[h+1, :] = (sum over its contributions (point i, remainder r) of bary[r,i] * [el_minus_gr[:, i] ; feat2[i, :]]) * inv,
+ *   inv = 1 / (sum of bary[r,i] + 1e-5) when `normalize`, else 1;  S[0, :] = 0 (the "-1 neighbour" sink row).
+ * Same result as efgh_bcl_zero + efgh_bcl_scatter + efgh_bcl_normalize up to the order of the float additions, with
+ * no atomics.  point_rows / vertex_offsets / contributions come from efgh_lattice_points_batch /
+ * efgh_lattice_vertices_batch of the same level.
+ *   feat2: point-major, C2 (% 4 == 0, <= 512) contiguous floats per point, point stride stride_n2; S has 4 + C2 columns;
+ *   rows: vertex CAPACITY - the h_cap given to the lattice calls (it locates the heavy-vertex list behind
+ *     vertex_offsets); rows_dev the device-side vertex count; inv_out (rows+1) optional. */
+int efgh_bcl_splat_gather(const float *point_rows, const float *feat2, int64_t stride_n2, int C2,
+                          const int32_t *vertex_offsets, const int32_t *contributions, int64_t rows,
+                          const int32_t *rows_dev, int normalize, float *S, int64_t ldS, float *inv_out, void *stream);
 
 /* One launch zero-fills what a BCL forward accumulates into.  With R = rows_dev ? min(*rows_dev, rows) : rows:
  *   S (R + rows_extra rows x C, leading dimension ldS) and wsum (R + rows_extra floats) - the splat targets,

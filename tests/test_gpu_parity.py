@@ -173,8 +173,9 @@ def test_bcl_enet_chain_vs_oracle(precision, dev, monkeypatch):
         prev = y
 
 
+@pytest.mark.parametrize("gather_splat", [True, False])
 @pytest.mark.parametrize("sensor,factor", [("os1-64-16k", 4.0), ("os1-64", 1.0)])
-def test_scan_pipeline_vs_oracle(sensor, factor, dev):
+def test_scan_pipeline_vs_oracle(sensor, factor, gather_splat, dev):
     """The sync-free whole-scan pipeline (what bench.py times): lattice dicts bit-exact against the C oracle,
     BCL outputs of all five levels within 1e-5 of the float64 oracle (config 1 and config 2 clouds)."""
     from efgh_b200.pipeline import ScanPipeline, make_enet_weights
@@ -182,7 +183,7 @@ def test_scan_pipeline_vs_oracle(sensor, factor, dev):
     pc = synth.synth_scan(4, sensor)
     N = pc.shape[1]
     weights = make_enet_weights(synth.ENET_BCL, seed=3)
-    pipe = ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=factor)
+    pipe = ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=factor, gather_splat=gather_splat)
     feat0 = torch.randn(32, N, generator=torch.Generator().manual_seed(1))
     for _ in range(2):  # twice: buffers are reused across scans
         pipe.enqueue(torch.from_numpy(pc).to(dev), feat0.to(dev))
@@ -208,8 +209,9 @@ def test_scan_pipeline_vs_oracle(sensor, factor, dev):
         gpu_prev = got_l.double()
 
 
+@pytest.mark.parametrize("gather_splat", [True, False])
 @pytest.mark.parametrize("sizes", [None, (16384, 5000, 1, 12001)])
-def test_batched_pipeline_matches_single_scans(sizes, dev):
+def test_batched_pipeline_matches_single_scans(sizes, gather_splat, dev):
     """Ragged batch: B scans through one launch sequence.  Per scan the lattice must equal the C oracle
     bit for bit (own hash table / key box / insertion order, local vertex numbering), and the BCL outputs must
     match the float64 oracle within the per-layer tolerance - i.e. batching changes nothing but the launch count."""
@@ -220,7 +222,7 @@ def test_batched_pipeline_matches_single_scans(sizes, dev):
     sizes = list(sizes) if sizes else [n] * B
     clouds = [synth.synth_scan(30 + b, "os1-64-16k")[:, :sizes[b]] for b in range(B)]
     weights = make_enet_weights(synth.ENET_BCL, seed=3)
-    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=B)
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=B, gather_splat=gather_splat)
     if sizes != [n] * B:
         pipe.set_scan_sizes(sizes)
     g = torch.Generator().manual_seed(2)

@@ -21,6 +21,7 @@ SIGNATURES = {
     "efgh_lattice_workspace_bytes": (sz, [i64]),
     "efgh_lattice_points": (i32, [vp, i64, i64, vp, f32, vp, vp, i64, i64, vp, vp, sz, vp]),
     "efgh_lattice_vertices": (i32, [i64, vp, vp, i64, vp, i32, i64, vp, vp, i64, vp, i64, f32, vp, vp, sz, vp]),
+    "efgh_lattice_table_entries": (i64, [i64, i64]),
     "efgh_lattice_batch_workspace_bytes": (sz, [i32, i64, i64]),
     "efgh_lattice_batch_info_ints": (i64, [i32]),
     "efgh_lattice_vertex_offsets_ints": (i64, [i64]),

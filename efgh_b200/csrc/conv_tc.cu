@@ -83,7 +83,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // Same, but yields issue slots between polls: used by roles whose wake-up latency is not critical (their
 // spin loops would otherwise compete with the producer warps on the same scheduler).
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 64) {
   uint32_t done = 0;
   while (true) {
     asm volatile(
@@ -96,7 +96,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
-    __nanosleep(64);
+    __nanosleep(ns);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -188,7 +188,13 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 // Optional timeline trace (debug): role r of CTA 0 appends (event, globaltimer) pairs to trace[r*kTraceCap...]
 constexpr int kTraceCap = 512;
+// Role timeline hook: compiled in only with -DEFGH_CONV_TRACE (tools/conv_tc_trace.py); the production kernel is
+// instruction-issue bound and every trace point costs four instructions per K chunk.
 __device__ __forceinline__ void trace_ev(unsigned long long *trace, int role, int &n, int ev) {
+#ifndef EFGH_CONV_TRACE
+  (void)trace; (void)role; (void)n; (void)ev;
+  return;
+#endif
   if (trace && blockIdx.x == 0 && n < kTraceCap) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -221,32 +227,35 @@ __device__ __forceinline__ void group_range(int n_chunks, int n_groups, int g, i
 
 // Position in one producer team's chunk sequence.  The CTA's chunks (all chunks of item blockIdx.x, then of
 // item blockIdx.x + gridDim.x, ...) are numbered 0, 1, 2, ...; team t takes numbers t, t+kTeams, ...
+// A team crosses into a new item every 1-2 chunks, so the crossing must be cheap: the chunk range of every K
+// group comes from a shared-memory table (gb[g] .. gb[g+1]) and item -> (tile, group) is advanced
+// incrementally (no integer division in the loop).
+constexpr int kMaxGroups = 256;
 struct TeamPos {
-  int item, j, j_end, tile;
+  int item, j, j_end, tile, g;
   __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
   // carry j >= j_end over into the following items
-  __device__ __forceinline__ void settle(const ConvParams &p, int n_items) {
+  __device__ __forceinline__ void settle(const ConvParams &p, int n_items, const int *gb, int dq, int dr) {
     while (item < n_items && j >= j_end) {
       const int over = j - j_end;
       item += (int)gridDim.x;
+      tile += dq; g += dr;
+      if (g >= p.n_groups) { g -= p.n_groups; ++tile; }
       if (item >= n_items) break;
-      int jb, je;
-      group_range(p.n_chunks, p.n_groups, item % p.n_groups, jb, je);
-      j = jb + over; j_end = je; tile = item / p.n_groups;
+      j = gb[g] + over; j_end = gb[g + 1];
     }
   }
-  __device__ __forceinline__ void init(const ConvParams &p, int n_items, int team) {
-    item = (int)blockIdx.x; j = j_end = tile = 0;
+  __device__ __forceinline__ void init(const ConvParams &p, int n_items, int team, const int *gb, int dq, int dr) {
+    item = (int)blockIdx.x; j = j_end = 0;
+    tile = item / p.n_groups; g = item - tile * p.n_groups;
     if (item < n_items) {
-      int jb, je;
-      group_range(p.n_chunks, p.n_groups, item % p.n_groups, jb, je);
-      j = jb + team; j_end = je; tile = item / p.n_groups;
-      settle(p, n_items);
+      j = gb[g] + team; j_end = gb[g + 1];
+      settle(p, n_items, gb, dq, dr);
     }
   }
-  __device__ __forceinline__ void advance(const ConvParams &p, int n_items) {
+  __device__ __forceinline__ void advance(const ConvParams &p, int n_items, const int *gb, int dq, int dr) {
     j += kTeams;
-    settle(p, n_items);
+    settle(p, n_items, gb, dq, dr);
   }
 };
 
@@ -267,8 +276,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   const uint32_t bar_a_full = smem_u32(bars), bar_a_empty = bar_a_full + 8 * 6, bar_b_full = bar_a_empty + 8 * 6,
                  bar_b_empty = bar_b_full + 8 * 4, bar_acc_full = bar_b_empty + 8 * 4, bar_acc_empty = bar_acc_full + 16;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 24);
+  int *s_gb = reinterpret_cast<int *>(bars + 26);        // [n_groups + 1] first chunk of every K group
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t spin_ns = ((uint32_t)p.dbg_flags >> 16 & 0xffu) * 8u;          // timing studies: sleep between polls
+  const uint32_t relax_ns = ((uint32_t)p.dbg_flags >> 24 & 0xffu) ? ((uint32_t)p.dbg_flags >> 24 & 0xffu) * 8u : 64u;
   const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
   const int n_tiles = (H + kTileM - 1) / kTileM;
   const int n_items = n_tiles * p.n_groups;
@@ -276,13 +288,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   constexpr uint32_t kAStageCols = NSPLIT == 3 ? 64 : 32;
   const uint32_t a_ring_col = (uint32_t)(p.acc_stages * p.nacc * N);
 
+  for (int i = threadIdx.x; i <= p.n_groups; i += kThreads) {
+    int gbeg = p.n_chunks, gend;
+    if (i < p.n_groups) group_range(p.n_chunks, p.n_groups, i, gbeg, gend);
+    s_gb[i] = gbeg;
+  }
+  const int it_dq = (int)gridDim.x / p.n_groups, it_dr = (int)gridDim.x % p.n_groups;   // item += gridDim.x in (tile, group) terms
   for (int i = threadIdx.x; i < N; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   if (p.in_bias)
     for (int i = threadIdx.x; i < p.C; i += kThreads) s_in_bias[i] = __ldg(p.in_bias + i);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 6; ++i) { mbar_init(bar_a_full + 8 * i, 128); mbar_init(bar_a_empty + 8 * i, 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(bar_a_full + 8 * i, 4); mbar_init(bar_a_empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full + 8 * a, 1); mbar_init(bar_acc_empty + 8 * a, 4); }
     fence_barrier_init();
   }
   if (warp == kTmaWarp) {
@@ -306,29 +324,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     const bool tracer = r == 0 && team < 2;
     int ntrace = 0;
 
-    // RAW neighbour indices (taps f, f+1) of this thread's vertex for the chunk at `pos`.  The loaded values are not
-    // touched here - any arithmetic on them would stall this in-order warp for the full L2 latency; they are decoded
-    // (+1, sink test) two chunks later, when they are used.  Encoding: with a neighbour table, raw = nbr (-1 = absent);
-    // without one (1x1 convolution), raw = own row or -1.
+    // Matrix rows (taps f, f+1) of this thread's vertex for the chunk at `pos`: neighbour index + 1, so 0 means
+    // "absent" and addresses the all-zero sink row; without a neighbour table (1x1 convolution) the vertex's own row,
+    // clamped into range (rows >= H are computed on garbage and dropped by the epilogue).  The loaded values are
+    // used two chunks later - any arithmetic on them right here would stall this in-order warp for the L2 latency,
+    // so the "+ 1" happens when they are shuffled out.
     auto fetch_rows = [&](const TeamPos &pos, int &ra, int &rb) {
       ra = rb = -1;
       if (!pos.valid(n_items)) return;
       const int h = pos.tile * kTileM + r;
+      if (!p.nbr) { ra = min(h, H - 1) - 1; return; }
       if (h >= H) return;
-      if (!p.nbr) { ra = h; return; }
       const int f = (int)__umulhi((uint32_t)(pos.j * kChunkK), p.magic_c);
       ra = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h);
       if (f + 1 < p.F) rb = load_idx<IdxT>(p.nbr, (f + 1) * p.nbr_ld + h);
     };
-    const int row_bias = p.nbr ? 1 : 0;                       // raw index -> matrix row (row 0 of a sink matrix = absent)
+    const uint32_t always = p.nbr ? 0u : 1u;                // without a sink row every (in-K) piece is copied
 
     TeamPos pi, pc, pp;                                     // issue / convert / row-prefetch positions
-    pi.init(p, n_items, team);
+    pi.init(p, n_items, team, s_gb, it_dq, it_dr);
     pc = pi; pp = pi;
     int r0a, r0b, r1a, r1b, r2a, r2b;                       // row pairs for pi, pi+1, pi+2
     fetch_rows(pp, r0a, r0b);
-    pp.advance(p, n_items); fetch_rows(pp, r1a, r1b);
-    pp.advance(p, n_items); fetch_rows(pp, r2a, r2b);
+    pp.advance(p, n_items, s_gb, it_dq, it_dr); fetch_rows(pp, r1a, r1b);
+    pp.advance(p, n_items, s_gb, it_dq, it_dr); fetch_rows(pp, r2a, r2b);
     uint32_t n_inflight = 0, slot_i = 0, slot_c = 0, a_ph = 0;
     bool st_pending = false;
 
@@ -348,27 +367,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         for (int i = 0; i < 8; ++i) {                         // all shuffles first: they pipeline
           const int R = 4 * i + (lane >> 3);
           const int ra = __shfl_sync(0xffffffffu, r0a, R), rb = __shfl_sync(0xffffffffu, r0b, R);
-          rows[i] = in_k ? (wrap ? rb : ra) : -1;               // raw; row = raw + row_bias, valid iff raw >= 0
+          rows[i] = (wrap ? rb : ra) + 1;                     // matrix row; 0 = absent (sink row)
         }
         if (tracer) trace_ev(p.trace, team, ntrace, 5);
         const uint32_t dst_lane = dst + ((uint32_t)lane >> 3) * 128u;
         const uint32_t u_lane = (uint32_t)lane & 7u;
+        const uint64_t xc = reinterpret_cast<uint64_t>(p.X + c_u);
+        const uint32_t ldx4 = (uint32_t)p.ldX * 4u;           // row pitch in bytes; rows * pitch < 2^32 (checked by the host)
+        const uint32_t kmask = in_k ? 0xffffffffu : 0u;
+        // Per copy: one IMAD (byte offset), one wide add (address), the zero-fill predicate - this loop is
+        // instruction-issue bound, a 64-bit multiply per row was a quarter of the kernel's instructions.
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t R7 = ((uint32_t)(4 * i) + ((uint32_t)lane >> 3)) & 7u;
-          const float *src = rows[i] >= 0 ? p.X + (int64_t)(rows[i] + row_bias) * p.ldX + c_u : p.X;
-          const uint32_t nbytes = rows[i] >= 0 ? 16u : 0u;
-          if (!(p.dbg_flags & 1))
+          const uint32_t nbytes = (((uint32_t)rows[i] | always) & kmask) ? 16u : 0u;   // absent neighbour / K padding: zero-fill
+          uint64_t src;
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(src) : "r"((uint32_t)rows[i]), "r"(ldx4), "l"(xc));
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_lane + (uint32_t)i * 512u + ((u_lane ^ R7) << 4)), "l"(src),
                        "r"(nbytes)
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (tracer) trace_ev(p.trace, team, ntrace, 6);
-        pi.advance(p, n_items);
+        pi.advance(p, n_items, s_gb, it_dq, it_dr);
         r0a = r1a; r0b = r1b; r1a = r2a; r1b = r2b;
         if (tracer) trace_ev(p.trace, team, ntrace, 7);
-        pp.advance(p, n_items); fetch_rows(pp, r2a, r2b);
+        pp.advance(p, n_items, s_gb, it_dq, it_dr); fetch_rows(pp, r2a, r2b);
         ++n_inflight;
         if (++slot_i == (uint32_t)p.raw_slots) slot_i = 0;
         if (tracer) trace_ev(p.trace, team, ntrace, 1);
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       if (st_pending) {                                     // previous chunk's TMEM stores had a whole issue to complete
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(bar_a_full + 8 * team);
+        { __syncwarp(); if (lane == 0) mbar_arrive(bar_a_full + 8 * team); }   // one arrival per warp: every arrival wakes the CTA's barrier sleepers
         st_pending = false;
       }
       if (n_inflight >= 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -414,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) big[i] = __float_as_uint(v[i]) & 0xffffe000u;
         if (!waited) {                                      // MMA done with this team's previous chunk
-          mbar_wait(bar_a_empty + 8 * team, a_ph ^ 1);
+          if (spin_ns) mbar_wait_relaxed(bar_a_empty + 8 * team, a_ph ^ 1, spin_ns); else mbar_wait(bar_a_empty + 8 * team, a_ph ^ 1);
           tc_fence_after();
           waited = true;
         }
@@ -425,27 +449,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           tmem_st16(a_t + 32 + 16 * hlf, big);
         }
       }
-      st_pending = true;
+      if (!(p.dbg_flags & 2)) {                             // publish at once: the MMA of this chunk gates the team's next A stage
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        { __syncwarp(); if (lane == 0) mbar_arrive(bar_a_full + 8 * team); }   // one arrival per warp: every arrival wakes the CTA's barrier sleepers
+      } else {
+        st_pending = true;
+      }
       a_ph ^= 1;
       if (tracer) trace_ev(p.trace, team, ntrace, 3);
-      pc.advance(p, n_items);
+      pc.advance(p, n_items, s_gb, it_dq, it_dr);
       --n_inflight;
       if (++slot_c == (uint32_t)p.raw_slots) slot_c = 0;
     }
     if (st_pending) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(bar_a_full + 8 * team);
+      { __syncwarp(); if (lane == 0) mbar_arrive(bar_a_full + 8 * team); }   // one arrival per warp: every arrival wakes the CTA's barrier sleepers
     }
   } else if (warp == kTmaWarp) {
     // ===================== weight loader (TMA bulk copies) =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int j_begin, j_end;
-        group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
+        const int gi = item % p.n_groups;
+        const int j_begin = s_gb[gi], j_end = s_gb[gi + 1];
         for (int j = j_begin; j < j_end; ++j) {
-          mbar_wait_relaxed(bar_b_empty + 8 * s, ph ^ 1);
+          mbar_wait_relaxed(bar_b_empty + 8 * s, ph ^ 1, relax_ns);
           mbar_arrive_expect_tx(bar_b_full + 8 * s, b_bytes);
           // several 8 KB copies in flight per stage: one large bulk copy is latency-bound
           for (uint32_t off = 0; off < b_bytes; off += 8192u)
@@ -465,8 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0, seq = 0;
       int ntrace = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
-        int j_begin, j_end;
-        group_range(p.n_chunks, p.n_groups, item % p.n_groups, j_begin, j_end);
+        const int gi = item % p.n_groups;
+        const int j_begin = s_gb[gi], j_end = s_gb[gi + 1];
         const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
         const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
         if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
@@ -531,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
       const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
       if (tracer) trace_ev(p.trace, 4, ntrace, 100 + (int)tcount);
-      mbar_wait_relaxed(bar_acc_full + 8 * as, aph);
+      mbar_wait_relaxed(bar_acc_full + 8 * as, aph, relax_ns);
       tc_fence_after();
       if (tracer) trace_ev(p.trace, 4, ntrace, 1);
       // Each thread holds 32 consecutive columns of ITS row after tcgen05.ld; going straight to global memory
@@ -599,7 +629,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         if (tracer) trace_ev(p.trace, 4, ntrace, 12);
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * as);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
       if (tracer) trace_ev(p.trace, 4, ntrace, 2);
     }
   }
@@ -671,13 +702,13 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   else if (2 * N <= room) { nacc = 1; acc_stages = 2; }
   if (acc_stages * nacc * N > room) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
-  const size_t budget = 224 * 1024 - 1024 - 256 - kEpiStageBytes - kBiasFloats * 4;
+  const size_t budget = 224 * 1024 - 1024 - 256 - (kMaxGroups + 4) * 4 - kEpiStageBytes - kBiasFloats * 4;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
   int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
   if (raw > kMaxRaw) raw = kMaxRaw;
   if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; p->nacc = nacc; }
-  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + 1024;
+  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + (kMaxGroups + 4) * 4 + 1024;
   return true;
 }
 
@@ -733,8 +764,11 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   p.n_chunks = (F * C + kChunkK - 1) / kChunkK;
   p.n_groups = efgh_bcl_conv_tc_groups(F * C);
   p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
+  EFGH_REQUIRE(p.n_groups <= kMaxGroups, "efgh_bcl_conv_tc: K=%d too long (%d K groups, at most %d)", F * C, p.n_groups, kMaxGroups);
   EFGH_REQUIRE(accumulate || p.n_groups == 1,
                "efgh_bcl_conv_tc: K=%d needs %d partial sums; call with accumulate=1 on a zero-filled Y", F * C, p.n_groups);
+  EFGH_REQUIRE((h + 1) * ldX < (1ll << 30), "efgh_bcl_conv_tc: X has %lld x %lld elements; the gather addresses rows with 32-bit byte offsets",
+               (long long)(h + 1), (long long)ldX);
   size_t smem = 0;
   conv_tc_plan(M, nsplit, &p, &smem);
   if ((g_conv_flags >> 4) & 15) p.raw_slots = min(p.raw_slots, (g_conv_flags >> 4) & 15);

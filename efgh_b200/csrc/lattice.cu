@@ -100,12 +100,11 @@ inline int64_t pow2_ceil(int64_t v) {
 
 inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-// n_cap: points of the whole launch; B scans of at most n_cap_scan points each (B = 1: n_cap_scan = n_cap)
-Workspace carve(void *base, int64_t n_cap, int B = 1, int64_t n_cap_scan = -1) {
+// n_cap: points of the whole launch; B scans with table_entries hash-table entries each (single scan: 8 per point)
+Workspace carve(void *base, int64_t n_cap, int B = 1, int64_t table_entries = -1) {
   Workspace w;
   if (n_cap < 1) n_cap = 1;
-  if (n_cap_scan < 1) n_cap_scan = n_cap;
-  w.table_cap = pow2_ceil(8 * n_cap_scan);               // per scan
+  w.table_cap = table_entries >= 1 ? pow2_ceil(table_entries) : pow2_ceil(8 * n_cap);   // per scan
   size_t off = 0;
   char *b = static_cast<char *>(base);
   w.table = reinterpret_cast<Entry *>(b + off); off = align_up(off + sizeof(Entry) * w.table_cap * B);
@@ -563,7 +562,9 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
       const int4 s = slots[i];
       const int v0 = table_all[s.x].index, v1 = table_all[s.y].index, v2 = table_all[s.z].index, v3 = table_all[s.w].index;
       if (loff) {
-        loff[i] = v0; loff[off_ld + i] = v1; loff[2 * off_ld + i] = v2; loff[3 * off_ld + i] = v3;
+        long long *lo = reinterpret_cast<long long *>(loff);
+        __stcs(lo + i, (long long)v0); __stcs(lo + off_ld + i, (long long)v1);
+        __stcs(lo + 2 * off_ld + i, (long long)v2); __stcs(lo + 3 * off_ld + i, (long long)v3);
       }
       if (loff32) {
         loff32[i] = v0; loff32[off_ld + i] = v1; loff32[2 * off_ld + i] = v2; loff32[3 * off_ld + i] = v3;
@@ -588,13 +589,15 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
                          {0.0f, 0.0f, EFGH_E_C3}};
 
   // Four threads per vertex, each owning taps g, g+4, g+8, ...: a thread keeps four independent table probes in
-  // flight (the probes are L2-latency bound) and stores to nbr[f, :] stay coalesced along the vertex index.
+  // flight (the probes are L2-latency bound).  A CTA round covers 64 consecutive vertices x 4 tap groups
+  // (thread = 64 g + vertex): stores to nbr[f, :] stay coalesced along the vertex index and all probes of a
+  // vertex - and of its scan - happen at the same time, so a batch's hash tables are walked one after the other
+  // instead of four times each.
   const bool want_nbr = F > 0 && (nbr || nbr32);
   const int groups = want_nbr ? 4 : 1;
-  const long long total = (long long)groups * H;
-  for (long long item = tid; item < total; item += stride) {
-    const int g = (int)(item / H);
-    const int h = (int)(item - (long long)g * H);
+  const int per_round = blockDim.x / groups;                // vertices per CTA round
+  const int g = threadIdx.x / per_round;
+  for (int h = blockIdx.x * per_round + (threadIdx.x - g * per_round); h < H; h += gridDim.x * per_round) {
     if (batched) {                                             // the vertex's own scan: its table, its key box
       const int scan = find_scan(s_start, bt.B, h);
       table = table_all + (long long)scan * bt.tstride;
@@ -661,7 +664,7 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
         for (int t = 0; t < 4; ++t) {
           const int f = f0 + 4 * t;
           if (f >= F) continue;
-          if (nbr) nbr[f * nbr_ld + h] = res[t];
+          if (nbr) __stcs(reinterpret_cast<long long *>(nbr) + f * nbr_ld + h, (long long)res[t]);   // reference-format copy: streamed past the L2
           if (nbr32) nbr32[f * nbr_ld + h] = res[t];
         }
       }
@@ -690,9 +693,17 @@ using namespace efgh;
 
 extern "C" size_t efgh_lattice_workspace_bytes(int64_t n_cap) { return carve(nullptr, n_cap).bytes; }
 
-extern "C" size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, int64_t n_cap_total) {
+extern "C" int64_t efgh_lattice_table_entries(int64_t n_scan, int64_t h_scan) {
+  if (n_scan < 1) n_scan = 1;
+  int64_t v = 4 * n_scan;                                 // a scan of n points has at most 4n vertices
+  if (h_scan >= 1 && h_scan < v) v = h_scan;
+  return pow2_ceil(2 * v);                                // load factor <= 0.5
+}
+
+extern "C" size_t efgh_lattice_batch_workspace_bytes(int B, int64_t table_entries, int64_t n_cap_total) {
   if (B < 1) B = 1;
-  return carve(nullptr, n_cap_total, B, n_cap_scan).bytes;
+  if (table_entries < 1) table_entries = 1;
+  return carve(nullptr, n_cap_total, B, table_entries).bytes;
 }
 
 extern "C" int64_t efgh_lattice_vertex_offsets_ints(int64_t h_cap) { return h_cap + 2 + kMaxHeavy; }
@@ -703,12 +714,12 @@ namespace {
 
 int lattice_points_impl(const char *who, const float *pts, int64_t pts_ld, int64_t n, const int32_t *n_dev, float scale,
                         float *barycentric, float *el_minus_gr, int64_t out_ld, int64_t h_cap, efgh_lattice_state *state,
-                        void *workspace, size_t workspace_bytes, void *stream, Batch bt, int64_t n_cap_scan) {
+                        void *workspace, size_t workspace_bytes, void *stream, Batch bt, int64_t table_entries) {
   EFGH_REQUIRE(n >= 0 && n < (1ll << 28), "%s: n=%lld out of range", who, (long long)n);
   EFGH_REQUIRE(state && workspace && (n == 0 || (pts && barycentric && el_minus_gr)), "%s: null pointer", who);
   EFGH_REQUIRE(pts_ld >= n && out_ld >= n, "%s: leading dimension smaller than n", who);
   const int B = bt.pt_start ? bt.B : 1;
-  Workspace w = carve(workspace, n, B, bt.pt_start ? n_cap_scan : n);
+  Workspace w = carve(workspace, n, B, bt.pt_start ? table_entries : -1);
   if (w.bytes > workspace_bytes) {
     set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, w.bytes);
     return EFGH_ENOMEM;
@@ -734,7 +745,7 @@ int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, i
                           const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
                           int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld, float next_divisor,
                           efgh_lattice_state *state, void *workspace, size_t workspace_bytes, void *stream, Batch bt,
-                          int64_t n_cap_scan) {
+                          int64_t table_entries) {
   EFGH_REQUIRE(n >= 0 && n < (1ll << 28) && h >= 0 && h < (1ll << 30), "%s: sizes out of range", who);
   EFGH_REQUIRE(state && workspace, "%s: null pointer", who);
   EFGH_REQUIRE(F <= 0 || filter_offsets, "%s: filter_offsets is null", who);
@@ -742,7 +753,7 @@ int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, i
   EFGH_REQUIRE((!blur_neighbors && !blur_neighbors32) || nbr_ld >= h, "%s: nbr_ld < h", who);
   EFGH_REQUIRE(!next_pts || next_ld >= h, "%s: next_ld < h", who);
   const int B = bt.pt_start ? bt.B : 1;
-  Workspace w = carve(workspace, n, B, bt.pt_start ? n_cap_scan : n);
+  Workspace w = carve(workspace, n, B, bt.pt_start ? table_entries : -1);
   if (w.bytes > workspace_bytes) {
     set_error("%s: workspace %zu < %zu bytes", who, workspace_bytes, w.bytes);
     return EFGH_ENOMEM;
@@ -761,10 +772,10 @@ int lattice_vertices_impl(const char *who, int64_t n, int64_t *lattice_offset, i
   return EFGH_OK;
 }
 
-int make_batch(const char *who, const int32_t *scan_start, int B, int64_t n_cap_scan, int32_t *batch_info, Batch *bt,
+int make_batch(const char *who, const int32_t *scan_start, int B, int64_t table_entries, int32_t *batch_info, Batch *bt,
                int32_t *voff, int32_t *contrib, float *point_rows, int64_t h_cap) {
   EFGH_REQUIRE(B >= 1 && B <= kMaxBatch, "%s: batch of %d scans (1..%d supported)", who, B, kMaxBatch);
-  EFGH_REQUIRE(scan_start && batch_info && n_cap_scan >= 1, "%s: null scan_start / batch_info or n_cap_scan < 1", who);
+  EFGH_REQUIRE(scan_start && batch_info && table_entries >= 1, "%s: null scan_start / batch_info or table_entries < 1", who);
   bt->pt_start = scan_start; bt->info = batch_info; bt->B = B;
   bt->tm_off = batch_tm_off(B); bt->box_off = batch_box_off(B); bt->tstride = 0;
   bt->voff = voff; bt->contrib = contrib; bt->cursor = nullptr; bt->point_rows = point_rows;
@@ -781,7 +792,7 @@ extern "C" int efgh_lattice_points(const float *pts, int64_t pts_ld, int64_t n, 
                                    void *stream) {
   Batch bt = {nullptr, nullptr, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
   return lattice_points_impl("efgh_lattice_points", pts, pts_ld, n, n_dev, scale, barycentric, el_minus_gr, out_ld, h_cap,
-                             state, workspace, workspace_bytes, stream, bt, n);
+                             state, workspace, workspace_bytes, stream, bt, -1);
 }
 
 extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
@@ -792,33 +803,33 @@ extern "C" int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t
   Batch bt = {nullptr, nullptr, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0};
   return lattice_vertices_impl("efgh_lattice_vertices", n, lattice_offset, lattice_offset32, off_ld, filter_offsets, F, h,
                                blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld, next_divisor, state, workspace,
-                               workspace_bytes, stream, bt, n);
+                               workspace_bytes, stream, bt, -1);
 }
 
 extern "C" int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start,
-                                         int B, int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr,
+                                         int B, int64_t table_entries, float scale, float *barycentric, float *el_minus_gr,
                                          int64_t out_ld, int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info,
                                          int32_t *vertex_offsets, float *point_rows, void *workspace, size_t workspace_bytes,
                                          void *stream) {
   Batch bt;
-  if (int rc = make_batch("efgh_lattice_points_batch", scan_start, B, n_cap_scan, batch_info, &bt, vertex_offsets, nullptr,
+  if (int rc = make_batch("efgh_lattice_points_batch", scan_start, B, table_entries, batch_info, &bt, vertex_offsets, nullptr,
                           point_rows, h_cap))
     return rc;
   return lattice_points_impl("efgh_lattice_points_batch", pts, pts_ld, n_cap_total, nullptr, scale, barycentric,
-                             el_minus_gr, out_ld, h_cap, state, workspace, workspace_bytes, stream, bt, n_cap_scan);
+                             el_minus_gr, out_ld, h_cap, state, workspace, workspace_bytes, stream, bt, table_entries);
 }
 
-extern "C" int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t n_cap_scan,
+extern "C" int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t table_entries,
                                            int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
                                            const int32_t *filter_offsets, int F, int64_t h, int64_t *blur_neighbors,
                                            int32_t *blur_neighbors32, int64_t nbr_ld, float *next_pts, int64_t next_ld,
                                            float next_divisor, efgh_lattice_state *state, int32_t *batch_info,
                                            int32_t *contributions, void *workspace, size_t workspace_bytes, void *stream) {
   Batch bt;
-  if (int rc = make_batch("efgh_lattice_vertices_batch", scan_start, B, n_cap_scan, batch_info, &bt, nullptr, contributions,
+  if (int rc = make_batch("efgh_lattice_vertices_batch", scan_start, B, table_entries, batch_info, &bt, nullptr, contributions,
                           nullptr, h))
     return rc;
   return lattice_vertices_impl("efgh_lattice_vertices_batch", n_cap_total, lattice_offset, lattice_offset32, off_ld,
                                filter_offsets, F, h, blur_neighbors, blur_neighbors32, nbr_ld, next_pts, next_ld,
-                               next_divisor, state, workspace, workspace_bytes, stream, bt, n_cap_scan);
+                               next_divisor, state, workspace, workspace_bytes, stream, bt, table_entries);
 }

@@ -83,7 +83,10 @@ class ScanPipeline(object):
                 F = self.gd.get_filter_size(radius)
                 h_cap = min(4 * n_cap, cap)
                 lv = {
-                    "n_cap_scan": n_cap_scan,
+                    # one scan's hash table: 4 x its vertex capacity (load factor <= 0.25), never more than 8 per point.
+                    # The tables of a whole batch should stay in the 126 MB L2 (8 scans x 8 MB); at 2 x capacity
+                    # (load ~0.4) the longer probe sequences were measured to cost more than the footprint saves.
+                    "table": int(self.L.efgh_lattice_table_entries(n_cap_scan, 2 * cap_scan)),
                     "info": torch.zeros(max(int(self.L.efgh_lattice_batch_info_ints(self.B)), 1), dtype=i32, device=dev),
                     "gs": self.gather_splat and li > 0,
                     "voff": torch.zeros(int(self.L.efgh_lattice_vertex_offsets_ints(h_cap)), dtype=i32, device=dev) if self.gather_splat and li > 0 else None,
@@ -122,7 +125,7 @@ class ScanPipeline(object):
                         lv[nm] = img
                     lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin) > 1
                 if self.batch_api:
-                    ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, n_cap_scan, n_cap))
+                    ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, lv["table"], n_cap))
                 else:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_workspace_bytes(n_cap))
                 self.levels.append(lv)
@@ -197,11 +200,11 @@ class ScanPipeline(object):
             if self.batch_api:
                 info = lv["info"].data_ptr()
                 timed("L%d.points" % li, lambda: ck(L.efgh_lattice_points_batch(
-                    pts_ptr, pts_ld, n_cap, seg, self.B, lv["n_cap_scan"], lv["scale"], lv["bary"].data_ptr(),
+                    pts_ptr, pts_ld, n_cap, seg, self.B, lv["table"], lv["scale"], lv["bary"].data_ptr(),
                     lv["elmgr"].data_ptr(), n_cap, h_cap, st, info, _capi.ptr(lv["voff"]), _capi.ptr(lv["prow"]), ws, wsn, s_lat),
                     "efgh_lattice_points_batch"))
                 timed("L%d.vertices" % li, lambda: ck(L.efgh_lattice_vertices_batch(
-                    n_cap, seg, self.B, lv["n_cap_scan"], _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap,
+                    n_cap, seg, self.B, lv["table"], _capi.ptr(lv["loff64"]), lv["loff32"].data_ptr(), n_cap,
                     lv["offs"].data_ptr(), lv["F"], h_cap, _capi.ptr(lv["nbr64"]), lv["nbr32"].data_ptr(), h_cap,
                     _capi.ptr(lv["next"]), h_cap, lv["divisor"], st, info, _capi.ptr(lv["contrib"]), ws, wsn, s_lat),
                     "efgh_lattice_vertices_batch"))

@@ -119,8 +119,10 @@ int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_o
  * The BCL entry points below then treat the whole batch as one lattice, unchanged.
  *   scan_start: (B+1) int32 ON THE DEVICE, ascending, scan_start[0] = 0, no empty scan; for level l+1 pass
  *     level l's vertex_start (= the first B+1 words of its batch_info);
- *   n_cap_scan: capacity (points) of ONE scan - sizes each scan's hash table; n_cap_total: capacity of the
- *     concatenated arrays (the true total is read from scan_start[B]);
+ *   table_entries: hash-table entries reserved for EACH scan, a power of two; efgh_lattice_table_entries(n, h)
+ *     gives the size for scans of at most n points / h vertices (2 x min(4n, h), i.e. load factor <= 0.5 - small
+ *     tables keep a whole batch's probes in the L2); a scan that outgrows its table sets EFGH_ST_TABLE_FULL;
+ *   n_cap_total: capacity of the concatenated arrays (the true total is read from scan_start[B]);
  *   batch_info: efgh_lattice_batch_info_ints(B) int32 on the device, written by efgh_lattice_points_batch
  *     (words [0, B] = vertex_start) and read by efgh_lattice_vertices_batch;
  *   state: totals over the batch (n, hash_cnt, status); its key box is unused. 1 <= B <= 64;
@@ -132,13 +134,14 @@ int efgh_lattice_vertices(int64_t n, int64_t *lattice_offset, int32_t *lattice_o
  *     lattice_offset32 to be requested too, and vertex_offsets to have been given to the points call of the level;
  *   point_rows (n_cap_total, 8) f32, optional: point-major copy [el_minus_gr[0..3], barycentric[0..3]] per point. */
 int64_t efgh_lattice_vertex_offsets_ints(int64_t h_cap);
-size_t efgh_lattice_batch_workspace_bytes(int B, int64_t n_cap_scan, int64_t n_cap_total);
+int64_t efgh_lattice_table_entries(int64_t n_scan, int64_t h_scan);
+size_t efgh_lattice_batch_workspace_bytes(int B, int64_t table_entries, int64_t n_cap_total);
 int64_t efgh_lattice_batch_info_ints(int B);
 int efgh_lattice_points_batch(const float *pts, int64_t pts_ld, int64_t n_cap_total, const int32_t *scan_start, int B,
-                              int64_t n_cap_scan, float scale, float *barycentric, float *el_minus_gr, int64_t out_ld,
+                              int64_t table_entries, float scale, float *barycentric, float *el_minus_gr, int64_t out_ld,
                               int64_t h_cap, efgh_lattice_state *state, int32_t *batch_info, int32_t *vertex_offsets,
                               float *point_rows, void *workspace, size_t workspace_bytes, void *stream);
-int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t n_cap_scan,
+int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, int B, int64_t table_entries,
                                 int64_t *lattice_offset, int32_t *lattice_offset32, int64_t off_ld,
                                 const int32_t *filter_offsets, int F, int64_t h,
                                 int64_t *blur_neighbors, int32_t *blur_neighbors32, int64_t nbr_ld,

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--sensor", default=SENSOR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print a per-stage timing table to stderr")
+    ap.add_argument("--stem", action="store_true",
+                    help="SURVEY §8 f1: compute E-Net's pointwise stem inside the level-0 splat; the cloud is then the only input")
     ap.add_argument("--atomic-splat", action="store_true", help="splat with vector atomics instead of the gather-form splat")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -202,9 +204,15 @@ def run_ours(args):
     # resident inputs, one (3, G*N) / (32, G*N) pair per group: scan b of the group in columns [b*N, (b+1)*N)
     pc_dev = [torch.from_numpy(np.concatenate(clouds[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
     ft_dev = [torch.from_numpy(np.concatenate(feats[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NG)]
-    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G, gather_splat=not args.atomic_splat) for _ in range(P)]
+    stem = None
+    if args.stem:   # random-init conv_in (reference nets/enet.py:24-28): 3 -> 32 -> 32 -> 32, LeakyReLU(0.1)
+        gs_ = torch.Generator().manual_seed(5)
+        stem = ([(torch.randn(co, ci, 1, generator=gs_) * 0.3, torch.randn(co, generator=gs_) * 0.1) for ci, co in ((3, 32), (32, 32), (32, 32))], True)
+        ft_dev = [None] * NG
+    pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G,
+                          gather_splat=not args.atomic_splat, stem=stem) for _ in range(P)]
     pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0,
-                                                 gather_splat=not args.atomic_splat)
+                                                 gather_splat=not args.atomic_splat, stem=stem)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
     main = torch.cuda.current_stream(dev)
 
@@ -293,13 +301,14 @@ def run_ours(args):
     e2e_steps = max(2, args.steps // 2)
     ms_e2e = timed_region(step_e2e, e2e_steps)
     e2e_value = B * world * e2e_steps / (ms_e2e * 1e-3)
-    h2d = B * (clouds[0].nbytes + feats[0].nbytes)
+    h2d = B * (clouds[0].nbytes + (feats[0].nbytes if stem is None else 0))
     d2h = NG * (out_pin[0].numel() * 4 + st_pin[0].numel() * 4 + (vs_pin[0].numel() * 4 if G > 1 else 0))
     assert int(st_pin[0][0, 1]) == counts[0] or NG > P  # the records really came back
 
     # ---- single-scan latency and per-stage table (outside the timed region)
     lat = []
-    pc1_dev, ft1_dev = pc_dev[0][:, :N].contiguous(), ft_dev[0][:, :N].contiguous()
+    pc1_dev = pc_dev[0][:, :N].contiguous()
+    ft1_dev = ft_dev[0][:, :N].contiguous() if stem is None else None
     g1 = pipe1.graph_for(pc1_dev, ft1_dev, streams[0]) if use_graph else None
     for _ in range(5):
         torch.cuda.synchronize(dev)
@@ -359,8 +368,12 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd" % (args.sensor, N),
                    "scans_per_gpu_per_step": B, "scans_per_launch_sequence": G, "concurrent_pipelines": P, "levels_H": counts_scan0,
-                   "l2_policy": "inputs larger than L2 (%d scans x %.1f MB resident, cycled)" % (B, (clouds[0].nbytes + feats[0].nbytes) / 1e6),
+                   "l2_policy": ("inputs larger than L2 (%d scans x %.1f MB resident, cycled)" % (B, (clouds[0].nbytes + feats[0].nbytes) / 1e6))
+                                if stem is None else
+                                ("working set larger than L2: every step streams %.0f MB of lattice / feature buffers (%d scans x %.0f MB algorithmic)"
+                                 % (B * total_bytes / 1e6, B, total_bytes / 1e6)),
                    "splat": "gather (vertex -> contributions lists)" if pipes[0].gather_splat else "atomic scatter",
+                   "stem": "conv_in fused into the level-0 splat (input = cloud only)" if stem is not None else "stem features are an input (32 x N f32)",
                    "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                    "algorithmic_MB_per_scan": total_bytes / 1e6,
                    "scan_roofline_frac": total_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},

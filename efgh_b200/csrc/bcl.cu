@@ -22,16 +22,45 @@ constexpr int kTP = 32;  // points per tile in scatter / gather
 // Two sources are concatenated along channels on the fly (reference nets/enet.py:113-137 materialises the
 // torch.cat); either may be channel-major (stride_n == 1) or point-major.
 // ---------------------------------------------------------------------------------------------
+// Pointwise stem fused into the splat's tile load (reference nets/enet.py:24-28,111 and
+// nets/net_utils.py:35-43): the second feature source is not read from memory but computed per point as
+// act(W3 act(W2 act(W1 p + b1) + b2) + b3), act = LeakyReLU(slope) (slope 0 = ReLU), from the point's cin
+// coordinates - the (32, N) stem output of E-Net never exists in HBM.
+// Packed weights: W1 (c1 x cin) b1 (c1) W2 (c2 x c1) b2 (c2) W3 (c3 x c2) b3 (c3), row-major, c* <= 32, cin <= 4.
+struct Stem {
+  const float *pts; int64_t pts_ld; const float *w; int cin, c1, c2, c3; float slope;
+};
+__host__ __device__ inline int stem_weight_floats(int cin, int c1, int c2, int c3) {
+  return c1 * cin + c1 + c2 * c1 + c2 + c3 * c2 + c3;
+}
+
 template <typename IdxT, int TP>
 __global__ void __launch_bounds__(256)
 k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const float *__restrict__ feat2, int64_t sc2,
           int64_t sn2, int C2, int n_host, const int32_t *n_dev, const float *__restrict__ w, int64_t w_ld,
-          const void *__restrict__ off, int64_t off_ld, int shift, float *S, int64_t ldS, float *wsum) {
+          const void *__restrict__ off, int64_t off_ld, int shift, float *S, int64_t ldS, float *wsum, Stem stem) {
   extern __shared__ float smem[];
   const int C = C1 + C2;
   float *tile = smem;                                   // [C][TP+1]
   float *s_w = smem + (size_t)C * (TP + 1);             // [4][TP]
   int *s_row = reinterpret_cast<int *>(s_w + 4 * TP);   // [4][TP]
+  float *s_stem = reinterpret_cast<float *>(s_row + 4 * TP);          // weights | pts [4][TP+1] | h1 [32][TP+1] | h2 [32][TP+1]
+  const int stem_nw = stem.pts ? stem_weight_floats(stem.cin, stem.c1, stem.c2, stem.c3) : 0;
+  if (stem.pts) {
+    // weights transposed to [k][o] so that a thread reads the 4 outputs it owns with one 16-byte broadcast load
+    int base = 0;
+    const int cins[3] = {stem.cin, stem.c1, stem.c2}, couts[3] = {stem.c1, stem.c2, stem.c3};
+    for (int l = 0; l < 3; ++l) {
+      const int ci = cins[l], co = couts[l];
+      for (int i = threadIdx.x; i < ci * co; i += blockDim.x) {
+        const int o = i / ci, k = i - o * ci;
+        s_stem[base + k * co + o] = __ldg(stem.w + base + i);
+      }
+      for (int i = threadIdx.x; i < co; i += blockDim.x) s_stem[base + ci * co + i] = __ldg(stem.w + base + ci * co + i);
+      base += ci * co + co;
+    }
+    __syncthreads();
+  }
   const int n = n_dev ? min(*n_dev, n_host) : n_host;
   const int n_tiles = (n + TP - 1) / TP;
   const bool vec = (C % 4 == 0) && (ldS % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
@@ -44,6 +73,39 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const 
       const int64_t fsc = src ? sc2 : sc, fsn = src ? sn2 : sn;
       const int Cs = src ? C2 : C1, c_off = src ? C1 : 0;
       if (Cs == 0) continue;
+      if (src == 1 && stem.pts) {
+        // three pointwise layers on the tile's points; layer outputs live in shared memory [channel][point]
+        float *s_p = s_stem + stem_nw, *s_h1 = s_p + 4 * (TP + 1), *s_h2 = s_h1 + 32 * (TP + 1);
+        const float *W1 = s_stem, *b1 = W1 + stem.c1 * stem.cin, *W2 = b1 + stem.c1, *b2 = W2 + stem.c2 * stem.c1,
+                    *W3 = b2 + stem.c2, *b3 = W3 + stem.c3 * stem.c2;
+        for (int idx = threadIdx.x; idx < stem.cin * TP; idx += blockDim.x) {
+          const int a = idx / TP, pt = idx % TP;
+          s_p[a * (TP + 1) + pt] = pt < np ? __ldg(stem.pts + a * stem.pts_ld + n0 + pt) : 0.f;
+        }
+        __syncthreads();
+        // thread = (point, group of 4 outputs): per input channel one activation read + one 16-byte weight read
+        auto layer = [&](const float *Wt, const float *b, int cin_l, int cout_l, const float *in, float *out, int out_ld) {
+          for (int idx = threadIdx.x; idx < (cout_l >> 2) * TP; idx += blockDim.x) {
+            const int og = idx / TP, pt = idx - og * TP;
+            float4 acc = *reinterpret_cast<const float4 *>(b + 4 * og);
+            for (int k = 0; k < cin_l; ++k) {
+              const float x = in[k * (TP + 1) + pt];
+              const float4 wv = *reinterpret_cast<const float4 *>(Wt + k * cout_l + 4 * og);
+              acc.x = fmaf(wv.x, x, acc.x); acc.y = fmaf(wv.y, x, acc.y); acc.z = fmaf(wv.z, x, acc.z); acc.w = fmaf(wv.w, x, acc.w);
+            }
+            float *o = out + (4 * og) * out_ld + pt;
+            o[0] = acc.x > 0.f ? acc.x : stem.slope * acc.x;
+            o[out_ld] = acc.y > 0.f ? acc.y : stem.slope * acc.y;
+            o[2 * out_ld] = acc.z > 0.f ? acc.z : stem.slope * acc.z;
+            o[3 * out_ld] = acc.w > 0.f ? acc.w : stem.slope * acc.w;
+          }
+          __syncthreads();
+        };
+        layer(W1, b1, stem.cin, stem.c1, s_p, s_h1, TP + 1);
+        layer(W2, b2, stem.c1, stem.c2, s_h1, s_h2, TP + 1);
+        layer(W3, b3, stem.c2, stem.c3, s_h2, tile + (size_t)c_off * (TP + 1), TP + 1);
+        continue;
+      }
       if (fsn == 1) {  // channel-major (C,N): coalesce along points
         for (int idx = threadIdx.x; idx < Cs * TP; idx += blockDim.x) {
           int c = idx / TP, p = idx % TP;
@@ -690,32 +752,61 @@ int dispatch_idx(int idx_bits, F &&f) {
 
 using namespace efgh;
 
-extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *feat2,
-                                int64_t stride_c2, int64_t stride_n2, int C2, int64_t n, const int32_t *n_dev,
-                                const float *w, int64_t w_ld, const void *off, int idx_bits, int64_t off_ld, int row_shift,
-                                float *S, int64_t ldS, float *wsum, void *stream) {
-  if (!feat2) C2 = 0;
-  EFGH_REQUIRE(C > 0 && C2 >= 0 && n >= 0 && n < (1ll << 30), "efgh_bcl_scatter: bad sizes C=%d C2=%d n=%lld", C, C2, (long long)n);
+namespace {
+int scatter_impl(const char *who, const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *feat2,
+                 int64_t stride_c2, int64_t stride_n2, int C2, int64_t n, const int32_t *n_dev, const float *w, int64_t w_ld,
+                 const void *off, int idx_bits, int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, Stem stem,
+                 void *stream) {
+  if (!feat2 && !stem.pts) C2 = 0;
+  EFGH_REQUIRE(C > 0 && C2 >= 0 && n >= 0 && n < (1ll << 30), "%s: bad sizes C=%d C2=%d n=%lld", who, C, C2, (long long)n);
   if (n == 0) return EFGH_OK;
-  EFGH_REQUIRE(feat && w && off && S, "efgh_bcl_scatter: null pointer");
+  EFGH_REQUIRE(feat && w && off && S, "%s: null pointer", who);
   // 32-point tiles when a channel-major source needs 128-byte coalescing along points; 8-point tiles otherwise
   // (four times as many CTAs - the deep levels have few points)
-  const bool wide = C >= C2 ? stride_n == 1 : stride_n2 == 1;   // layout of the wider source decides
+  const bool wide = stem.pts ? true : (C >= C2 ? stride_n == 1 : stride_n2 == 1);   // layout of the wider source decides
   const int TP = wide ? 32 : 8;
-  const size_t smem = sizeof(float) * ((size_t)(C + C2) * (TP + 1) + 4 * TP) + sizeof(int) * 4 * TP;
-  EFGH_REQUIRE(smem <= 200 * 1024, "efgh_bcl_scatter: C=%d too large", C + C2);
+  size_t smem = sizeof(float) * ((size_t)(C + C2) * (TP + 1) + 4 * TP) + sizeof(int) * 4 * TP;
+  if (stem.pts) smem += sizeof(float) * (stem_weight_floats(stem.cin, stem.c1, stem.c2, stem.c3) + (4 + 64) * (TP + 1));
+  EFGH_REQUIRE(smem <= 200 * 1024, "%s: C=%d too large", who, C + C2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dispatch_idx(idx_bits, [&](auto tag) -> int {
     using IdxT = decltype(tag);
     auto launch = [&](auto kern) -> int {
       if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kern<<<grid_for((n + TP - 1) / TP, 1, 8), 256, smem, s>>>(feat, stride_c, stride_n, C, feat2, stride_c2, stride_n2, C2, (int)n,
-                                                                 n_dev, w, w_ld, off, off_ld, row_shift, S, ldS, wsum);
+                                                                 n_dev, w, w_ld, off, off_ld, row_shift, S, ldS, wsum, stem);
       EFGH_LAUNCH_CHECK();
       return EFGH_OK;
     };
     return wide ? launch(k_scatter<IdxT, 32>) : launch(k_scatter<IdxT, 8>);
   });
+}
+}  // namespace
+
+extern "C" int efgh_bcl_scatter(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *feat2,
+                                int64_t stride_c2, int64_t stride_n2, int C2, int64_t n, const int32_t *n_dev,
+                                const float *w, int64_t w_ld, const void *off, int idx_bits, int64_t off_ld, int row_shift,
+                                float *S, int64_t ldS, float *wsum, void *stream) {
+  Stem none = {nullptr, 0, nullptr, 0, 0, 0, 0, 0.f};
+  return scatter_impl("efgh_bcl_scatter", feat, stride_c, stride_n, C, feat2, stride_c2, stride_n2, C2, n, n_dev, w, w_ld, off,
+                      idx_bits, off_ld, row_shift, S, ldS, wsum, none, stream);
+}
+
+extern "C" int64_t efgh_bcl_stem_weight_floats(int c_in, int c1, int c2, int c3) { return stem_weight_floats(c_in, c1, c2, c3); }
+
+extern "C" int efgh_bcl_scatter_stem(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *pts,
+                                     int64_t pts_ld, int c_in, int c1, int c2, int c3, const float *stem_weights,
+                                     float leaky_slope, int64_t n, const int32_t *n_dev, const float *w, int64_t w_ld,
+                                     const void *off, int idx_bits, int64_t off_ld, int row_shift, float *S, int64_t ldS,
+                                     float *wsum, void *stream) {
+  EFGH_REQUIRE(pts && stem_weights && pts_ld >= n, "efgh_bcl_scatter_stem: null pts / weights or pts_ld < n");
+  EFGH_REQUIRE(c_in >= 1 && c_in <= 4 && c1 >= 4 && c1 <= 32 && c2 >= 4 && c2 <= 32 && c3 >= 4 && c3 <= 32 &&
+                   c1 % 4 == 0 && c2 % 4 == 0 && c3 % 4 == 0,
+               "efgh_bcl_scatter_stem: stem widths %d -> %d -> %d -> %d (inputs <= 4, layers multiples of 4 up to 32)", c_in, c1, c2, c3);
+  EFGH_REQUIRE(C % 4 == 0, "efgh_bcl_scatter_stem: C=%d must be a multiple of 4 (shared-memory alignment of the stem weights)", C);
+  Stem st = {pts, pts_ld, stem_weights, c_in, c1, c2, c3, leaky_slope};
+  return scatter_impl("efgh_bcl_scatter_stem", feat, stride_c, stride_n, C, nullptr, 0, 0, c3, n, n_dev, w, w_ld, off, idx_bits,
+                      off_ld, row_shift, S, ldS, wsum, st, stream);
 }
 
 extern "C" int efgh_bcl_splat_gather(const float *point_rows, const float *feat2, int64_t stride_n2, int C2,

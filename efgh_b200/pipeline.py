@@ -34,7 +34,7 @@ _ACT = {"none": 0, "relu": 1, "leaky": 2}
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
                  vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
-                 precision="3xtf32", batch=1, gather_splat=True):
+                 precision="3xtf32", batch=1, gather_splat=True, stem=None):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
         vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
@@ -42,6 +42,9 @@ class ScanPipeline(object):
         gather_splat: levels >= 1 (whose input features are the previous level's point-major output rows) splat
         through the vertex -> contributions lists of the lattice build - no atomics, zero-fill and normalisation
         fused.  Level 0 (channel-major (C, N) input, working set beyond the L2 in batch mode) keeps the atomic scatter;
+        stem: None, or ([(W1, b1), (W2, b2), (W3, b3)], use_leaky) - E-Net's pointwise `conv_in` (reference
+        nets/enet.py:24-28; W as Conv1d weights (out, in, 1)): the level-0 splat then COMPUTES the stem features from
+        the cloud (SURVEY.md §8 f1) and enqueue() ignores feat0;
         batch: scans per launch sequence, each of n_points points (inputs are then (3, batch*n_points) /
         (C, batch*n_points), scan b in columns [b*n_points, (b+1)*n_points))."""
         self.dev = torch.device(device)
@@ -49,6 +52,15 @@ class ScanPipeline(object):
         self.B = int(batch)
         assert 1 <= self.B <= 64
         self.gather_splat = bool(gather_splat)
+        self.stem = None
+        if stem is not None:
+            layers, leaky = stem
+            assert len(layers) == 3
+            dims = [int(layers[0][0].shape[1])] + [int(W.shape[0]) for W, _ in layers]
+            assert dims[3] == stem_channels and all(int(W.shape[1]) == dims[i] for i, (W, _) in enumerate(layers))
+            flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for W, b in layers for t in (W, b)])
+            assert flat.numel() == self.L.efgh_bcl_stem_weight_floats(*dims)
+            self.stem = {"dims": dims, "w": flat.to(self.dev).contiguous(), "slope": 0.1 if leaky else 0.0}
         self.batch_api = self.B > 1 or self.gather_splat       # the batch entry points also serve a batch of one
         self.n_scan = int(n_points)
         self.n0 = int(n_points) * self.B
@@ -165,7 +177,7 @@ class ScanPipeline(object):
         L, ck = self.L, _capi.check
         main = stream if stream is not None else torch.cuda.current_stream(self.dev)
         s = main.cuda_stream
-        assert pc.shape[-1] == self.n0 and pc.stride(-1) == 1 and feat0.stride(-1) == 1
+        assert pc.shape[-1] == self.n0 and pc.stride(-1) == 1 and (self.stem is not None or feat0.stride(-1) == 1)
         ws, wsn = self.ws.data_ptr(), self.ws.numel()
         lat = None
         if self.overlap_lattice and timers is None:
@@ -188,7 +200,10 @@ class ScanPipeline(object):
             timers.setdefault(name, []).append((a, b))
 
         pts_ptr, pts_ld = pc.data_ptr(), pc.stride(0)
-        prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
+        if self.stem is not None:
+            prev_ptr, prev_sc, prev_sn, prev_c = None, 0, 1, self.stem["dims"][3]
+        else:
+            prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
         n_dev = None
         seg = self.scan_start.data_ptr()                      # batched: point-stream boundaries of the level
         if self.batch_api:
@@ -237,8 +252,16 @@ class ScanPipeline(object):
                                                lv["contrib"].data_ptr(), h_cap, h_dev, 1 if self.use_norm else 0, S, cin,
                                                None, s), "efgh_bcl_splat_gather")
                     return
-                # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat
-                ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev,
+                if li == 0 and self.stem is not None:
+                    # [el_minus_gr ; conv_in(xyz)]: the stem's three pointwise layers run on the splat's shared-memory tile
+                    d = self.stem["dims"]
+                    ck(L.efgh_bcl_scatter_stem(lv["elmgr"].data_ptr(), n_cap, 1, 4, pc.data_ptr(), pc.stride(0), d[0], d[1], d[2], d[3],
+                                               self.stem["w"].data_ptr(), self.stem["slope"], n_cap, n_dev, lv["bary"].data_ptr(),
+                                               n_cap, lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
+                                               lv["wsum"].data_ptr() if self.use_norm else None, s), "efgh_bcl_scatter_stem")
+                else:
+                  # [el_minus_gr (4 ch, channel-major) ; previous features] -> one scatter, no torch.cat
+                  ck(L.efgh_bcl_scatter(lv["elmgr"].data_ptr(), n_cap, 1, 4, prev_ptr, prev_sc, prev_sn, prev_c, n_cap, n_dev,
                                       lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
                                       lv["wsum"].data_ptr() if self.use_norm else None, s), "efgh_bcl_scatter")
                 if self.use_norm:
@@ -276,7 +299,7 @@ class ScanPipeline(object):
     def graph_for(self, pc, feat0, stream):
         """CUDA graph of enqueue(pc, feat0) (captured once per input-buffer pair, then replayed): the ~55 launches
         of a scan become one graph launch, which removes the per-launch host cost and most inter-kernel gaps."""
-        key = (pc.data_ptr(), feat0.data_ptr())
+        key = (pc.data_ptr(), feat0.data_ptr() if feat0 is not None else 0)
         g = self._graphs.get(key)
         if g is None:
             self.enqueue(pc, feat0, stream=stream)          # warm-up outside capture (function attributes, lazy init)
@@ -299,19 +322,21 @@ class ScanPipeline(object):
             if isinstance(pc_host, (list, tuple)):
                 n = self.n_scan
                 for b in range(self.B):                     # one strided DMA per matrix (no staging buffer)
-                    for dst, src in ((self._pc_dev, pc_host[b]), (self._feat_dev, feat_host[b])):
+                    for dst, src in ((self._pc_dev, pc_host[b]),) + (((self._feat_dev, feat_host[b]),) if self.stem is None else ()):
                         assert src.is_contiguous() and src.dtype == torch.float32 and src.shape[1] <= n
                         _capi.check(self.L.efgh_copy_matrix_async(dst.data_ptr() + 4 * self._starts0[b], dst.stride(0),
                                                                   src.data_ptr(), src.shape[1], src.shape[0], src.shape[1],
                                                                   1, st.cuda_stream), "efgh_copy_matrix_async")
             else:
                 self._pc_dev.copy_(pc_host, non_blocking=True)
-                self._feat_dev.copy_(feat_host, non_blocking=True)
+                if self.stem is None:
+                    self._feat_dev.copy_(feat_host, non_blocking=True)
+            fdev = self._feat_dev if self.stem is None else None      # fused stem: the cloud is the only input
             if use_graph:
-                self.graph_for(self._pc_dev, self._feat_dev, st).replay()
+                self.graph_for(self._pc_dev, fdev, st).replay()
                 Z = self.levels[-1]["Z"]
             else:
-                Z = self.enqueue(self._pc_dev, self._feat_dev, stream=st)
+                Z = self.enqueue(self._pc_dev, fdev, stream=st)
             out_host.copy_(Z[:out_host.shape[0]], non_blocking=True)
             state_host.copy_(self.states, non_blocking=True)
             if starts_host is not None:

@@ -157,6 +157,19 @@ int efgh_lattice_vertices_batch(int64_t n_cap_total, const int32_t *scan_start, 
  * layout work.  idx_bits is 64 (reference int64 tensors) or 32.
  * ---------------------------------------------------------------------------------------------- */
 
+/* efgh_bcl_scatter with E-Net's pointwise stem fused in (reference nets/enet.py:24-28,111,
+ * nets/net_utils.py:35-43): the second feature source is COMPUTED per point,
+ *   act(W3 act(W2 act(W1 p + b1) + b2) + b3),  act = LeakyReLU(leaky_slope) (0 = ReLU),  p = pts[0..c_in, i],
+ * so `conv_in`'s (1, 32, N) output and the torch.cat with el_minus_gr never exist in memory.  The matrix gets
+ * C + c3 columns.  stem_weights (device): W1 (c1 x c_in) b1 (c1) W2 (c2 x c1) b2 (c2) W3 (c3 x c2) b3 (c3),
+ * row-major = the Conv1d weights' (out, in, 1) layout; efgh_bcl_stem_weight_floats gives the length.
+ * pts: (c_in, n) rows with stride pts_ld - the UNSCALED cloud (reference enet.py:109-111).  c_in <= 4, layers <= 32. */
+int64_t efgh_bcl_stem_weight_floats(int c_in, int c1, int c2, int c3);
+int efgh_bcl_scatter_stem(const float *feat, int64_t stride_c, int64_t stride_n, int C, const float *pts, int64_t pts_ld,
+                          int c_in, int c1, int c2, int c3, const float *stem_weights, float leaky_slope, int64_t n,
+                          const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
+                          int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream);
+
 /* Gather-form splat + density normalisation in one pass (reference nets/bilateralNN.py:176-211, with E-Net's input
  * wiring `cat(el_minus_gr, previous features)`, reference nets/enet.py:113-137): for every vertex h
  *   S[h+1, :] = (sum over its contributions (point i, remainder r) of bary[r,i] * [el_minus_gr[:, i] ; feat2[i, :]]) * inv,

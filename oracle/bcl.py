@@ -45,3 +45,16 @@ def bcl_forward(features, in_bary, in_off, nbrs, convs, *, use_norm=True, do_spl
     if slice_bias is not None:                      # :260-261
         out = out + slice_bias.to(dt)
     return out.t()[None]
+
+
+def stem_forward(pc, layers, leaky=True, dtype=torch.float64):
+    """E-Net stem, reference nets/enet.py:24-28,111 + nets/net_utils.py:35-43: three pointwise Conv1d(k=1), each
+    followed by LeakyReLU(0.1) (use_leaky) or ReLU, on the UNSCALED cloud.  pc (3, N); layers [(W (out,in[,1]), b)]*3.
+    Returns (c3, N)."""
+    x = torch.as_tensor(pc).to(dtype)
+    for W, b in layers:
+        W = torch.as_tensor(W).to(dtype)
+        W = W[:, :, 0] if W.dim() == 3 else W
+        x = W @ x + torch.as_tensor(b).to(dtype)[:, None]
+        x = torch.where(x > 0, x, 0.1 * x) if leaky else torch.clamp(x, min=0)
+    return x

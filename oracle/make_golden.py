@@ -125,5 +125,32 @@ def main():
         print("bcl", name, tuple(out.shape), float(out.abs().mean()))
 
 
+def stem_golden():
+    """E-Net stem (reference nets/enet.py:24-28,111: three conv_1x1 of nets/net_utils.py:35-43 on the unscaled xyz)
+    -> tests/golden/stem_{leaky,relu}.npz: weights, input cloud, output of the LIVE reference modules on CPU."""
+    import torch.nn as nn
+    nu = ref_harness.load_net_utils()
+    os.makedirs(OUT, exist_ok=True)
+    pc = synth.synth_scan(12, "os1-64-16k")[:, :700]
+    for name, leaky in (("leaky", True), ("relu", False)):
+        torch.manual_seed(7 if leaky else 8)
+        stem = nn.Sequential(nu.conv_1x1(3, 32, use_leaky=leaky), nu.conv_1x1(32, 32, use_leaky=leaky),
+                             nu.conv_1x1(32, 32, use_leaky=leaky))
+        for prm in stem.parameters():                    # the reference's N(0, 1e-3) init gives ~0 outputs
+            torch.nn.init.normal_(prm, 0, 0.5)
+        with torch.no_grad():
+            out = stem(torch.from_numpy(pc.copy())[None])[0]
+        blob = {"pc": pc, "out": out.numpy(), "leaky": np.int64(leaky)}
+        for li in range(3):
+            blob["W%d" % li] = stem[li][0].weight.detach().numpy()
+            blob["b%d" % li] = stem[li][0].bias.detach().numpy()
+        np.savez_compressed(os.path.join(OUT, "stem_%s.npz" % name), **blob)
+        print("stem", name, tuple(out.shape), float(out.abs().mean()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-stem" in sys.argv:
+        stem_golden()
+    else:
+        main()
+        stem_golden()

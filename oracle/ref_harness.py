@@ -79,3 +79,15 @@ def load():
         _mods["g"] = _imp("generate_data")
         _mods["b"] = _imp("bilateralNN")
     return _mods["t"], _mods["g"], _mods["b"]
+
+
+def load_net_utils():
+    """The live reference's nets/net_utils.py (conv_1x1: the E-Net stem's building block, nets/enet.py:24-28)."""
+    if not available():
+        raise RuntimeError("reference not present at %s" % REF_ROOT)
+    if "n" not in _mods:
+        spec = importlib.util.spec_from_file_location("refnets_net_utils", os.path.join(REF_ROOT, "nets", "net_utils.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _mods["n"] = m
+    return _mods["n"]

@@ -286,6 +286,41 @@ def test_batched_forward_host_matches_enqueue(dev):
         assert H.rel_err(out.numpy(), want_Z.numpy()) < 1e-6          # same kernels; only the atomics' order differs
 
 
+@pytest.mark.parametrize("name,batch", [("leaky", 1), ("relu", 1), ("leaky", 3)])
+def test_fused_stem_pipeline(name, batch, dev, golden_dir):
+    """E-Net's pointwise stem computed inside the level-0 splat.  Level-0 BCL output with the stem fused
+    (only the cloud goes in) must match the float64 oracle fed with the reference-golden stem weights:
+    oracle stem -> cat(el_minus_gr, stem) -> oracle BCL, within the per-layer tolerance."""
+    import os
+    from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+    from oracle import lattice as ol, bcl as obcl
+    g = np.load(os.path.join(golden_dir, "stem_%s.npz" % name))
+    leaky = bool(g["leaky"])
+    layers = [(torch.from_numpy(g["W%d" % i]), torch.from_numpy(g["b%d" % i])) for i in range(3)]
+    # the oracle's stem itself is pinned to the live reference's output (tests/test_oracle_golden.py); here on a full cloud
+    n = 16384
+    clouds = [synth.synth_scan(50 + b, "os1-64-16k") for b in range(batch)]
+    weights = make_enet_weights(synth.ENET_BCL, seed=4)
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=batch, stem=(layers, leaky))
+    pc_all = torch.from_numpy(np.concatenate(clouds, axis=1)).to(dev)
+    for _ in range(2):
+        pipe.enqueue(pc_all, None)
+    pipe.counts()
+    for b in range(batch):
+        want = ol.generate(clouds[b], synth.SCALE_MAP)
+        stem64 = obcl.stem_forward(clouds[b], layers, leaky=leaky, dtype=torch.float64)
+        prev = stem64[None]
+        outs = pipe.outputs(scan=b) if batch > 1 else pipe.outputs()
+        for li, w in enumerate(want[:2]):
+            args = (torch.from_numpy(w["pc1_barycentric"]), torch.from_numpy(w["pc1_lattice_offset"]),
+                    torch.from_numpy(w["pc1_blur_neighbors"]), weights[li])
+            ref = obcl.bcl_forward(torch.cat((torch.from_numpy(w["pc1_el_minus_gr"]).double(), prev), 1), *args, dtype=torch.float64)
+            got_l = outs[li].cpu()
+            e = H.rel_err(got_l.numpy(), ref.numpy())
+            assert e < PER_LAYER_TOL, "fused stem, scan %d level %d rel err %g" % (b, li, e)
+            prev = got_l.double()
+
+
 # ------------------------------------------------------------------------------------------------
 # wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
 # ------------------------------------------------------------------------------------------------

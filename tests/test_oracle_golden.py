@@ -1,4 +1,6 @@
 """CPU: the oracle (oracle/) against the golden vectors generated from the live reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -100,3 +102,17 @@ def test_oracle_vs_live_reference_random():
         for li, (gg, w) in enumerate(zip(got, ref)):
             w = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in w.items()}
             H.assert_level_equal(gg, w, "n=%d L%d" % (n, li))
+
+
+@pytest.mark.parametrize("name", ["leaky", "relu"])
+def test_stem_oracle_vs_reference_golden(name, golden_dir):
+    """oracle.bcl.stem_forward (E-Net conv_in, reference nets/enet.py:24-28,111) against the output of the live
+    reference's nets/net_utils.py conv_1x1 stack stored by oracle/make_golden.py."""
+    import numpy as np
+    import torch
+    from oracle import bcl as obcl
+    g = np.load(os.path.join(golden_dir, "stem_%s.npz" % name))
+    layers = [(g["W%d" % i], g["b%d" % i]) for i in range(3)]
+    got = obcl.stem_forward(g["pc"], layers, leaky=bool(g["leaky"]), dtype=torch.float32).numpy()
+    assert got.shape == g["out"].shape
+    assert np.abs(got - g["out"]).max() <= 2e-6 * np.abs(g["out"]).max()

@@ -277,9 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
                  bar_b_empty = bar_b_full + 8 * 4, bar_acc_full = bar_b_empty + 8 * 4, bar_acc_empty = bar_acc_full + 16;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 24);
   int *s_gb = reinterpret_cast<int *>(bars + 26);        // [n_groups + 1] first chunk of every K group
+  int *s_rx = s_gb + kMaxGroups + 4 + (threadIdx.x >> 5) * 64;   // per producer warp: row indices of the chunk being issued (2 taps x 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t spin_ns = ((uint32_t)p.dbg_flags >> 16 & 0xffu) * 8u;          // timing studies: sleep between polls
+  // producers poll their TMEM A stage's barrier with a sleep in between: the polling loops were 18 % of the kernel's
+  // instructions (flags bits 16-23 override, 0xff = hardware try_wait loop without sleeping)
+  const uint32_t spin_f = (uint32_t)p.dbg_flags >> 16 & 0xffu;
+  const uint32_t spin_ns = spin_f == 0xffu ? 0u : (spin_f ? spin_f * 8u : 128u);
   const uint32_t relax_ns = ((uint32_t)p.dbg_flags >> 24 & 0xffu) ? ((uint32_t)p.dbg_flags >> 24 & 0xffu) * 8u : 64u;
   const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
   const int n_tiles = (H + kTileM - 1) / kTileM;
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       ra = load_idx<IdxT>(p.nbr, f * p.nbr_ld + h);
       if (f + 1 < p.F) rb = load_idx<IdxT>(p.nbr, (f + 1) * p.nbr_ld + h);
     };
+
     const uint32_t always = p.nbr ? 0u : 1u;                // without a sink row every (in-K) piece is copied
 
     TeamPos pi, pc, pp;                                     // issue / convert / row-prefetch positions
@@ -362,25 +367,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         const bool wrap = cu >= p.C;
         const int c_u = wrap ? cu - p.C : cu;
         const bool in_k = k0 + 4 * (lane & 7) < K;
+        // The 8 lanes of a row group need the row index held by the lane that owns the row: exchanged through 256
+        // bytes of warp-private shared memory (2 stores + 8 loads instead of 16 shuffles + 8 selects).
+        __syncwarp();
+        s_rx[lane] = r0a + 1;                                 // matrix row; 0 = absent neighbour = the all-zero sink row
+        s_rx[32 + lane] = r0b + 1;
+        __syncwarp();
+        const int *rx = s_rx + (wrap ? 32 : 0) + (lane >> 3);
         int rows[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                         // all shuffles first: they pipeline
-          const int R = 4 * i + (lane >> 3);
-          const int ra = __shfl_sync(0xffffffffu, r0a, R), rb = __shfl_sync(0xffffffffu, r0b, R);
-          rows[i] = (wrap ? rb : ra) + 1;                     // matrix row; 0 = absent (sink row)
-        }
+        for (int i = 0; i < 8; ++i) rows[i] = rx[4 * i];
         if (tracer) trace_ev(p.trace, team, ntrace, 5);
         const uint32_t dst_lane = dst + ((uint32_t)lane >> 3) * 128u;
         const uint32_t u_lane = (uint32_t)lane & 7u;
         const uint64_t xc = reinterpret_cast<uint64_t>(p.X + c_u);
         const uint32_t ldx4 = (uint32_t)p.ldX * 4u;           // row pitch in bytes; rows * pitch < 2^32 (checked by the host)
         const uint32_t kmask = in_k ? 0xffffffffu : 0u;
-        // Per copy: one IMAD (byte offset), one wide add (address), the zero-fill predicate - this loop is
-        // instruction-issue bound, a 64-bit multiply per row was a quarter of the kernel's instructions.
+        // Per copy: one wide multiply-add (address) and the zero-fill predicate - this loop is instruction-issue bound;
+        // a 64-bit multiply per row was a quarter of the kernel's instructions.  Absent neighbours (row 0) and K padding
+        // are zero-FILLED (source size 0), never read: copying the sink row instead was measured 6x slower - every SM
+        // hammering the same 144 bytes serialises in one L2 slice.
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t R7 = ((uint32_t)(4 * i) + ((uint32_t)lane >> 3)) & 7u;
-          const uint32_t nbytes = (((uint32_t)rows[i] | always) & kmask) ? 16u : 0u;   // absent neighbour / K padding: zero-fill
+          const uint32_t nbytes = (((uint32_t)rows[i] | always) & kmask) ? 16u : 0u;
           uint64_t src;
           asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(src) : "r"((uint32_t)rows[i]), "r"(ldx4), "l"(xc));
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_lane + (uint32_t)i * 512u + ((u_lane ^ R7) << 4)), "l"(src),
@@ -437,6 +447,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         uint32_t big[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) big[i] = __float_as_uint(v[i]) & 0xffffe000u;
+        if (NSPLIT == 1 && (p.dbg_flags & 4)) {             // probe: hand the tensor core unmasked fp32 (does kind::tf32 truncate?)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) big[i] = __float_as_uint(v[i]);
+        }
         if (!waited) {                                      // MMA done with this team's previous chunk
           if (spin_ns) mbar_wait_relaxed(bar_a_empty + 8 * team, a_ph ^ 1, spin_ns); else mbar_wait(bar_a_empty + 8 * team, a_ph ^ 1);
           tc_fence_after();
@@ -702,13 +716,13 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   else if (2 * N <= room) { nacc = 1; acc_stages = 2; }
   if (acc_stages * nacc * N > room) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
-  const size_t budget = 224 * 1024 - 1024 - 256 - (kMaxGroups + 4) * 4 - kEpiStageBytes - kBiasFloats * 4;
+  const size_t budget = 224 * 1024 - 1024 - 256 - (kMaxGroups + 4) * 4 - kProducerWarps * 256 - kEpiStageBytes - kBiasFloats * 4;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
   int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
   if (raw > kMaxRaw) raw = kMaxRaw;
   if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; p->nacc = nacc; }
-  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + (kMaxGroups + 4) * 4 + 1024;
+  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + (kMaxGroups + 4) * 4 + kProducerWarps * 256 + 1024;
   return true;
 }
 

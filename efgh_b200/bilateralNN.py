@@ -99,8 +99,9 @@ def gather(Z, row_scale, w, off, row_shift, bias, n):
     return out
 
 
-def conv(X, nbr, Wt, bias, act, h):
-    """X (rows, C) (already normalised); nbr (1,F,h) or None; Wt (F*C, M) -> Y (h, M)."""
+def conv(X, nbr, Wt, bias, act, h, wkey=None):
+    """X (rows, C) (already normalised); nbr (1,F,h) or None; Wt (F*C, M) -> Y (h, M).
+    wkey: the parameter Wt was derived from (the packed tensor-core image is cached on it)."""
     C = X.shape[1]
     M = Wt.shape[1]
     Y = torch.empty((h, M), dtype=torch.float32, device=X.device)
@@ -113,9 +114,7 @@ def conv(X, nbr, Wt, bias, act, h):
     nsplit = _NSPLIT.get(CONV_PRECISION, 0)
     if nsplit and L.efgh_bcl_conv_tc_supported(C, F, M, nsplit) and X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0:
         K = Wt.shape[0]
-        img = torch.empty(L.efgh_bcl_packed_weight_bytes(K, M, nsplit) // 4, dtype=torch.float32, device=X.device)
-        _capi.check(L.efgh_bcl_pack_weights(Wt.data_ptr(), K, M, nsplit, img.data_ptr(), _capi.stream_ptr()),
-                    "efgh_bcl_pack_weights")
+        img = _cached("img", wkey if wkey is not None else Wt, nsplit, lambda: _tc_image(Wt, nsplit))
         split = L.efgh_bcl_conv_tc_groups(K) > 1        # long contraction: partial sums are added in L2
         if split:
             Y.zero_()
@@ -252,15 +251,33 @@ def conv_wgrad(X, row_scale, nbr, dY, act_out, act, want_bias):
     return dWt, db
 
 
+# Re-laid weights ((K, M) matrices and the tensor-core kernel's packed images) are cached ON the parameter object, per
+# parameter VERSION: torch bumps `_version` on every in-place update (optimizer step, load_state_dict), so inference
+# re-uses them call after call, training rebuilds them once per step, and the cache dies with the parameter.
+def _cached(kind, W, extra, build):
+    cache = getattr(W, "_efgh_cache", None)
+    if cache is None or cache[0] != W._version:
+        cache = (W._version, {})
+        try:
+            W._efgh_cache = cache
+        except Exception:       # not an attribute-carrying tensor: just rebuild every call
+            return build()
+    d = cache[1]
+    key = (kind, extra)
+    if key not in d:
+        d[key] = build()
+    return d[key]
+
+
 def _wt_first(W):
     """Conv2d weight (M, C, F, 1) -> (F*C, M) row-major, k = f*C + c."""
     M, C, F, _ = W.shape
-    return W[:, :, :, 0].permute(2, 1, 0).reshape(F * C, M).contiguous()
+    return _cached("first", W, None, lambda: W.detach()[:, :, :, 0].permute(2, 1, 0).reshape(F * C, M).contiguous())
 
 
 def _wt_point(W):
     """Conv2d 1x1 weight (M, C, 1, 1) -> (C, M)."""
-    return W[:, :, 0, 0].t().contiguous()
+    return _cached("point", W, None, lambda: W.detach()[:, :, 0, 0].t().contiguous())
 
 
 class _BCLFunction(torch.autograd.Function):
@@ -291,7 +308,7 @@ class _BCLFunction(torch.autograd.Function):
                 W, b = wb[2 * k], wb[2 * k + 1]
                 Wt = _wt_first(W) if k == 0 else _wt_point(W)
                 act = _ACT["relu"] if k < nconv - 1 else final_act
-                Y = conv(X, nb, Wt, b, act, H)
+                Y = conv(X, nb, Wt, b, act, H, wkey=W)
                 xs.append(X); ys.append(Y); wts.append(Wt); acts.append(act)
                 X, nb = Y, None
             if do_slice:

@@ -32,6 +32,9 @@ _ACT = {"none": 0, "relu": 1, "leaky": 2}
 #   "fp32"   CUDA-core FFMA kernel (also the automatic choice for shapes the tensor-core kernel rejects).
 CONV_PRECISION = os.environ.get("EFGH_CONV_PRECISION", "3xtf32")
 _NSPLIT = {"3xtf32": 3, "tf32": 1}
+# Data gradient of the convolutions as a gather-form convolution on the tensor-core kernel (else the scatter-form
+# CUDA-core kernel).
+DGRAD_ON_TENSOR_CORES = os.environ.get("EFGH_DGRAD", "tc") != "scatter"
 
 
 def init_weights(m):
@@ -180,7 +183,7 @@ def neighbours_symmetric(nbr, mirror):
     return bool(((back == here) | (nb < 0)).all())
 
 
-def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit):
+def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit, symmetric=None):
     """Data gradient of one convolution on the tensor-core kernel, or None when the shape does not fit it.
 
     The scatter form dX[nbr[f,h]+1, c] += sum_m dY[h,m] W[m,c,f] becomes, through the lattice's symmetry
@@ -211,7 +214,9 @@ def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit):
     F = nb2.shape[0]
     if rem % 4 or Cg == 0 or not L.efgh_bcl_conv_tc_supported(Mk, F, Cg, nsplit):
         return None
-    if not neighbours_symmetric(nbr, mirror):
+    if symmetric is None:
+        symmetric = neighbours_symmetric(nbr, mirror)
+    if not symmetric:
         return None
     Xp = torch.empty((h + 1, Mk), dtype=torch.float32, device=dY.device)
     Xp[0].zero_()                                                     # the sink row: absent neighbours
@@ -322,6 +327,7 @@ class _BCLFunction(torch.autograd.Function):
         ctx.has_slice_bias = slice_bias is not None
         ctx.save_for_backward(in_bary, in_off, nbr, out_bary, out_off, inv, *xs, *ys, *wts, *wb[0::2])
         ctx.nconv = nconv
+        ctx.nbr_symmetric = getattr(nbr, "_efgh_symmetric", None)     # set by GenerateData when it already knows
         return out
 
     @staticmethod
@@ -370,8 +376,9 @@ class _BCLFunction(torch.autograd.Function):
                     dY = None
                     break
                 dX = None
-                if nsplit:
-                    dX = conv_dgrad_tc(dY, act_out, act, nbr if first else None, Ws[k], mirror, X.shape[0], nsplit)
+                if nsplit and DGRAD_ON_TENSOR_CORES:
+                    dX = conv_dgrad_tc(dY, act_out, act, nbr if first else None, Ws[k], mirror, X.shape[0], nsplit,
+                                       symmetric=ctx.nbr_symmetric)
                 if dX is None:
                     dX = conv_dgrad(dY, act_out, act, nbr if first else None, wts[k], X.shape[1], X.shape[0])
                 dY = dX

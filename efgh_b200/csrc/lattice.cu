@@ -537,7 +537,7 @@ __device__ __forceinline__ long long floor_mod64(long long a, long long b) {
 }
 
 __global__ void __launch_bounds__(256)
-k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
+k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
            const Entry *__restrict__ table_all, const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
            int64_t off_ld, const int32_t *__restrict__ foffs, int F, int64_t *__restrict__ nbr,
            int32_t *__restrict__ nbr32, int64_t nbr_ld, float *__restrict__ next_pts, int64_t next_ld,
@@ -611,16 +611,17 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
     int k[4];
     unpack_key(vkeys[h], k[0], k[1], k[2]);
     k[3] = -(k[0] + k[1] + k[2]);
+    bool aliased = false;
     if (want_nbr) {
       for (int f0 = g; f0 < F; f0 += 16) {
         unsigned long long want[4];
         unsigned hh[4];
         int res[4];
-        bool live[4];
+        bool live[4], ali[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int f = f0 + 4 * t;
-          live[t] = false; res[t] = -1; want[t] = 0; hh[t] = 0;
+          live[t] = false; ali[t] = false; res[t] = -1; want[t] = 0; hh[t] = 0;
           if (f >= F) continue;
           const int4 o = __ldg(reinterpret_cast<const int4 *>(foffs) + f);
           int q[4] = {k[0] + o.x, k[1] + o.y, k[2] + o.z, k[3] + o.w};
@@ -637,6 +638,7 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
             const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
             const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
             q[0] = (int)P + kmin[0]; q[1] = (int)a1 + kmin[1]; q[2] = (int)a2 + kmin[2]; q[3] = (int)a3 + kmin[3];
+            ali[t] = true;
           }
           if (q[0] + q[1] + q[2] + q[3] != 0) continue;        // not a lattice point: cannot be in the table
           want[t] = pack_key(q[0], q[1], q[2]);
@@ -659,6 +661,8 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
             idx = e2.w;
           }
           res[t] = cur == want[t] ? idx : -1;
+          if (ali[t] && res[t] >= 0) aliased = true;           // an out-of-box key aliased onto an existing vertex:
+                                                               // the neighbour table loses its mirror symmetry
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -669,6 +673,7 @@ k_vertices(const efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, cons
         }
       }
     }
+    if (aliased) atomicOr(&st->status, EFGH_ST_ALIASED);
     if (next_pts && g == 0) {                                // generate_data.py:177-178
       float q[4];
 #pragma unroll

@@ -40,7 +40,11 @@ class VertexCapExceeded(LatticeStatusError):
     pass
 
 
+ST_ALIASED = 8      # informational bit of efgh_lattice_state.status (include/efgh_b200.h)
+
+
 def check_status(status, level):
+    status &= ~ST_ALIASED
     if status:
         why = []
         if status & 1:
@@ -171,6 +175,9 @@ class GenerateData(object):
                     d[k] = d[k][:, :, :n_true]
                 if filt[li] > 0:
                     d["pc1_blur_neighbors"] = d["pc1_blur_neighbors"][:, :, :H]
+                    # no aliased lookup -> the table is mirror-symmetric: BilateralConvFlex.backward may use the
+                    # gather-form data gradient without checking on the device
+                    d["pc1_blur_neighbors"]._efgh_symmetric = not (int(host[li, 2]) & ST_ALIASED)
                 n_true = H
         self.last_states = states
         return out

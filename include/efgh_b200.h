@@ -45,6 +45,9 @@ extern "C" {
 #define EFGH_ST_KEY_RANGE 1   /* a lattice coordinate fell outside +-2^20: cloud far outside the supported box */
 #define EFGH_ST_VERTEX_CAP 2  /* more distinct vertices than the caller's capacity */
 #define EFGH_ST_TABLE_FULL 4  /* hash table capacity exhausted (workspace sized for fewer points) */
+#define EFGH_ST_ALIASED 8     /* informational, not an error: a neighbour key outside the key box was looked up through the
+                                 reference's mixed-radix key2int aliasing (transforms.py:62-78), so blur_neighbors may not
+                                 be symmetric (tap f of h is g  <=>  tap mirror(f) of g is h).  Clear = symmetric. */
 
 /* Device-resident per-level record; the caller may copy it back (24 x int32) after the level. */
 typedef struct {

@@ -321,6 +321,33 @@ def test_fused_stem_pipeline(name, batch, dev, golden_dir):
             prev = got_l.double()
 
 
+def test_neighbour_symmetry_flag(dev):
+    """GenerateData(exact=False) tags blur_neighbors with `_efgh_symmetric` (status bit EFGH_ST_ALIASED clear): whenever
+    the tag says symmetric, the brute-force device check must agree - BilateralConvFlex.backward relies on it to use
+    the gather-form data gradient.  Tiny / degenerate clouds are the ones whose neighbour keys leave the key box."""
+    from efgh_b200.generate_data import GenerateData, blur_offsets
+    from efgh_b200.bilateralNN import neighbours_symmetric
+    offs = [tuple(o) for o in blur_offsets(1, 3).tolist()]
+    mirror = tuple(offs.index(tuple(-v for v in o)) for o in offs)
+    rng = np.random.default_rng(0)
+    seen = {True: 0, False: 0}
+    clouds = [rng.standard_normal((3, n)).astype(np.float32) * s for n, s in ((2, 1.0), (5, 0.01), (7, 3.0), (33, 100.0), (300, 0.5), (4000, 20.0))]
+    clouds.append(synth.synth_scan(3, "os1-64-16k"))
+    for pc in clouds:
+        gd = GenerateData(3, synth.SCALE_MAP, "cuda", exact=False)
+        _, data = gd(torch.from_numpy(pc).to(dev))
+        for d in data:
+            nbr = d["pc1_blur_neighbors"]
+            tag = getattr(nbr, "_efgh_symmetric", None)
+            if tag is None:                 # sparse cloud: GenerateData fell back to exact mode, which does not tag
+                continue
+            seen[bool(tag)] += 1
+            if tag:
+                assert neighbours_symmetric(nbr, mirror)
+    print("symmetric-tagged levels: %d, aliased levels: %d" % (seen[True], seen[False]))
+    assert seen[True] > 0
+
+
 # ------------------------------------------------------------------------------------------------
 # wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
 # ------------------------------------------------------------------------------------------------

@@ -36,9 +36,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
-    ap.add_argument("--streams", type=int, default=2, help="concurrent scan pipelines per GPU")
-    ap.add_argument("--scan-batch", type=int, default=8,
+    ap.add_argument("--batch", type=int, default=32, help="scans per GPU per step")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="concurrent COMPUTE streams per GPU (the end-to-end leg always double-buffers its copies on separate streams)")
+    ap.add_argument("--scan-batch", type=int, default=16,
                     help="scans per launch sequence (ragged batched lattices, SURVEY §8 f2); 1 = one launch sequence per scan")
     ap.add_argument("--sensor", default=SENSOR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,7 +194,8 @@ def run_ours(args):
     if B % G:
         raise SystemExit("bench.py: --batch must be a multiple of --scan-batch")
     NG = B // G                                         # launch sequences ("groups") per step
-    P = max(1, min(args.streams, NG))
+    P = max(1, min(args.streams, NG))                   # compute streams
+    NP = max(P, min(NG, 2))                             # pipelines (buffer sets): >= 2 so that copies of one batch overlap kernels of another
     weights = make_enet_weights(synth.ENET_BCL)
     # this rank's scans: global scan index = rank + world * j  (scan-index sharding)
     seeds = [rank + world * j for j in range(B)]
@@ -210,16 +212,17 @@ def run_ours(args):
         stem = ([(torch.randn(co, ci, 1, generator=gs_) * 0.3, torch.randn(co, generator=gs_) * 0.1) for ci, co in ((3, 32), (32, 32), (32, 32))], True)
         ft_dev = [None] * NG
     pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G,
-                          gather_splat=not args.atomic_splat, stem=stem) for _ in range(P)]
+                          gather_splat=not args.atomic_splat, stem=stem) for _ in range(NP)]
     pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0,
                                                  gather_splat=not args.atomic_splat, stem=stem)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
+    copy_streams = [torch.cuda.Stream(dev) for _ in range(NP)]
     main = torch.cuda.current_stream(dev)
 
     use_graph = not args.no_graph
     graphs = None
     if use_graph:   # one CUDA graph per resident group (captures the whole 5-level launch sequence on that group's stream)
-        graphs = [pipes[j % P].graph_for(pc_dev[j], ft_dev[j], streams[j % P]) for j in range(NG)]
+        graphs = [pipes[j % NP].graph_for(pc_dev[j], ft_dev[j], streams[j % P]) for j in range(NG)]
 
     def step(timers=None):
         for j in range(NG):
@@ -227,7 +230,7 @@ def run_ours(args):
                 with torch.cuda.stream(streams[j % P]):
                     graphs[j].replay()
             else:
-                pipes[j % P].enqueue(pc_dev[j], ft_dev[j], stream=streams[j % P], timers=timers)
+                pipes[j % NP].enqueue(pc_dev[j], ft_dev[j], stream=streams[j % P], timers=timers)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -239,11 +242,11 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
-        for st in streams:
+        for st in streams + copy_streams:
             st.wait_event(e0)
         for _ in range(steps):
             fn()
-        for st in streams:
+        for st in streams + copy_streams:
             ev = torch.cuda.Event()
             ev.record(st)
             main.wait_event(ev)
@@ -290,11 +293,14 @@ def run_ours(args):
 
     def step_e2e():
         for j in range(NG):
+            # copies on the pipeline's own stream, kernels on a shared compute stream: H2D of batch j+1 overlaps batch j
             if G == 1:
-                pipes[j % P].forward_host(pc_pin[j], ft_pin[j], out_pin[j], st_pin[j], stream=streams[j % P], use_graph=use_graph)
+                pipes[j % NP].forward_host(pc_pin[j], ft_pin[j], out_pin[j], st_pin[j], stream=copy_streams[j % NP],
+                                           use_graph=use_graph, compute_stream=streams[j % P])
             else:
-                pipes[j % P].forward_host(pc_pin[j * G:(j + 1) * G], ft_pin[j * G:(j + 1) * G], out_pin[j], st_pin[j],
-                                          stream=streams[j % P], use_graph=use_graph, starts_host=vs_pin[j])
+                pipes[j % NP].forward_host(pc_pin[j * G:(j + 1) * G], ft_pin[j * G:(j + 1) * G], out_pin[j], st_pin[j],
+                                           stream=copy_streams[j % NP], use_graph=use_graph, starts_host=vs_pin[j],
+                                           compute_stream=streams[j % P])
 
     for _ in range(2):
         step_e2e()
@@ -303,7 +309,7 @@ def run_ours(args):
     e2e_value = B * world * e2e_steps / (ms_e2e * 1e-3)
     h2d = B * (clouds[0].nbytes + (feats[0].nbytes if stem is None else 0))
     d2h = NG * (out_pin[0].numel() * 4 + st_pin[0].numel() * 4 + (vs_pin[0].numel() * 4 if G > 1 else 0))
-    assert int(st_pin[0][0, 1]) == counts[0] or NG > P  # the records really came back
+    assert int(st_pin[0][0, 1]) == counts[0] or NG > NP  # the records really came back
 
     # ---- single-scan latency and per-stage table (outside the timed region)
     lat = []
@@ -367,7 +373,7 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd" % (args.sensor, N),
-                   "scans_per_gpu_per_step": B, "scans_per_launch_sequence": G, "concurrent_pipelines": P, "levels_H": counts_scan0,
+                   "scans_per_gpu_per_step": B, "scans_per_launch_sequence": G, "compute_streams": P, "pipelines": NP, "levels_H": counts_scan0,
                    "l2_policy": ("inputs larger than L2 (%d scans x %.1f MB resident, cycled)" % (B, (clouds[0].nbytes + feats[0].nbytes) / 1e6))
                                 if stem is None else
                                 ("working set larger than L2: every step streams %.0f MB of lattice / feature buffers (%d scans x %.0f MB algorithmic)"

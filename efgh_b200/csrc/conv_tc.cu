@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
         const uint32_t dst_lane = dst + ((uint32_t)lane >> 3) * 128u;
         const uint32_t u_lane = (uint32_t)lane & 7u;
         const uint64_t xc = reinterpret_cast<uint64_t>(p.X + c_u);
-        const uint32_t ldx4 = (uint32_t)p.ldX * 4u;           // row pitch in bytes; rows * pitch < 2^32 (checked by the host)
+        const uint32_t ldx4 = (uint32_t)p.ldX * 4u;           // row pitch in bytes (32-bit); mad.wide.u32 forms the full 64-bit offset
         const uint32_t kmask = in_k ? 0xffffffffu : 0u;
         // Per copy: one wide multiply-add (address) and the zero-fill predicate - this loop is instruction-issue bound;
         // a 64-bit multiply per row was a quarter of the kernel's instructions.  Absent neighbours (row 0) and K padding
@@ -781,8 +781,7 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   EFGH_REQUIRE(p.n_groups <= kMaxGroups, "efgh_bcl_conv_tc: K=%d too long (%d K groups, at most %d)", F * C, p.n_groups, kMaxGroups);
   EFGH_REQUIRE(accumulate || p.n_groups == 1,
                "efgh_bcl_conv_tc: K=%d needs %d partial sums; call with accumulate=1 on a zero-filled Y", F * C, p.n_groups);
-  EFGH_REQUIRE((h + 1) * ldX < (1ll << 30), "efgh_bcl_conv_tc: X has %lld x %lld elements; the gather addresses rows with 32-bit byte offsets",
-               (long long)(h + 1), (long long)ldX);
+  EFGH_REQUIRE(ldX < (1ll << 30), "efgh_bcl_conv_tc: ldX too large");   // row pitch in bytes fits 32 bits; mad.wide.u32 gives the 64-bit offset
   size_t smem = 0;
   conv_tc_plan(M, nsplit, &p, &smem);
   if ((g_conv_flags >> 4) & 15) p.raw_slots = min(p.raw_slots, (g_conv_flags >> 4) & 15);

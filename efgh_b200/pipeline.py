@@ -310,14 +310,19 @@ class ScanPipeline(object):
             self._graphs[key] = g
         return g
 
-    def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None, use_graph=False, starts_host=None):
+    def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None, use_graph=False, starts_host=None,
+                     compute_stream=None):
         """End-to-end call on HOST buffers (pinned for async copies): H2D of the cloud and stem features,
         the whole scan, D2H of the level records and of the first out_host.shape[0] rows of the last
         level's output.  Everything is enqueued on `stream`; synchronise it before reading the outputs.
         Batched pipelines take lists of B per-scan host tensors ((3,n) / (C,n) each) - or one (3, B*n) / (C, B*n)
         tensor already in batch layout - and, if given, fill starts_host (nlev, B+1) int32 with every level's
-        per-scan vertex boundaries."""
+        per-scan vertex boundaries.
+        compute_stream: run the kernels there while the copies stay on `stream` - two pipelines with their own copy
+        streams and ONE shared compute stream overlap PCIe transfers with kernels without letting the kernels of
+        different batches compete for the SMs and the L2."""
         st = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        cs = compute_stream if compute_stream is not None else st
         with torch.cuda.stream(st):
             if isinstance(pc_host, (list, tuple)):
                 n = self.n_scan
@@ -331,12 +336,22 @@ class ScanPipeline(object):
                 self._pc_dev.copy_(pc_host, non_blocking=True)
                 if self.stem is None:
                     self._feat_dev.copy_(feat_host, non_blocking=True)
-            fdev = self._feat_dev if self.stem is None else None      # fused stem: the cloud is the only input
+        if cs is not st:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cs.wait_event(ev)
+        fdev = self._feat_dev if self.stem is None else None      # fused stem: the cloud is the only input
+        with torch.cuda.stream(cs):
             if use_graph:
-                self.graph_for(self._pc_dev, fdev, st).replay()
+                self.graph_for(self._pc_dev, fdev, cs).replay()
                 Z = self.levels[-1]["Z"]
             else:
-                Z = self.enqueue(self._pc_dev, fdev, stream=st)
+                Z = self.enqueue(self._pc_dev, fdev, stream=cs)
+        if cs is not st:
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            st.wait_event(ev)
+        with torch.cuda.stream(st):
             out_host.copy_(Z[:out_host.shape[0]], non_blocking=True)
             state_host.copy_(self.states, non_blocking=True)
             if starts_host is not None:

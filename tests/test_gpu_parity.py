@@ -348,6 +348,40 @@ def test_neighbour_symmetry_flag(dev):
     assert seen[True] > 0
 
 
+@pytest.mark.parametrize("batch", [1, 2])
+def test_gather_splat_heavy_vertices(batch, dev):
+    """A much coarser second level gives its vertices hundreds of contributions each: the gather-form splat's
+    CTA-per-vertex path (more than 128 contributions) and its per-warp path must both match the oracle."""
+    from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+    from oracle import lattice as ol, bcl as obcl
+    smap = [[2.0, 1], [0.05, 1]]
+    plan = [(36, [32, 32]), (36, [32, 32])]
+    n = 8192
+    clouds = [synth.synth_scan(60 + b, "os1-64-16k")[:, :n] for b in range(batch)]
+    weights = make_enet_weights(plan, seed=6)
+    pipe = ScanPipeline(n, smap, plan, weights, dev, vertex_cap_factor=4.0, batch=batch)
+    g = torch.Generator().manual_seed(3)
+    feats = [torch.randn(32, n, generator=g) for _ in range(batch)]
+    pipe.enqueue(torch.from_numpy(np.concatenate(clouds, 1)).to(dev), torch.cat(feats, 1).to(dev))
+    pipe.counts()
+    heavy = int(pipe.levels[1]["voff"][pipe.levels[1]["h_cap"] + 1])
+    assert heavy > 0, "test cloud produced no heavy vertex"
+    for b in range(batch):
+        want = ol.generate(clouds[b], smap)
+        got = _to_np(pipe.level_dicts(scan=b) if batch > 1 else pipe.level_dicts())
+        outs = pipe.outputs(scan=b) if batch > 1 else pipe.outputs()
+        prev = feats[b][None].double()
+        for li, w in enumerate(want):
+            H.assert_level_equal(got[li], w, "heavy scan %d L%d" % (b, li))
+            ref = obcl.bcl_forward(torch.cat((torch.from_numpy(w["pc1_el_minus_gr"]).double(), prev), 1),
+                                   torch.from_numpy(w["pc1_barycentric"]), torch.from_numpy(w["pc1_lattice_offset"]),
+                                   torch.from_numpy(w["pc1_blur_neighbors"]), weights[li], dtype=torch.float64)
+            got_l = outs[li].cpu()
+            e = H.rel_err(got_l.numpy(), ref.numpy())
+            assert e < PER_LAYER_TOL, "heavy scan %d level %d rel err %g" % (b, li, e)
+            prev = got_l.double()
+
+
 # ------------------------------------------------------------------------------------------------
 # wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
 # ------------------------------------------------------------------------------------------------

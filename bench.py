@@ -366,7 +366,8 @@ def run_ours(args):
             "peak_source": peaks["source"] + " copy bandwidth",
             "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes, "tensor_tflops": dom_flops / (dom_ms * 1e-3) / 1e12,
             "share_of_scan": stages.get(DOM, 0.0) / max(sum(stages.values()), 1e-9),
-            "note": "latency-bound gather over an L2-resident matrix; FLOPs are 3x this figure on the tensor pipe (3xTF32)"}
+            "note": "instruction-issue bound (profiles/r1_conv_tc_stalls_batch8_v2.txt): 62 % of issue slots, L2 hit rate 85 %, "
+                    "DRAM traffic 1.3x algorithmic; FLOPs are 3x this figure on the tensor pipe (3xTF32)"}
     scan_ms = ms / (B * args.steps)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -378,7 +379,7 @@ def run_ours(args):
                                 if stem is None else
                                 ("working set larger than L2: every step streams %.0f MB of lattice / feature buffers (%d scans x %.0f MB algorithmic)"
                                  % (B * total_bytes / 1e6, B, total_bytes / 1e6)),
-                   "splat": "gather (vertex -> contributions lists)" if pipes[0].gather_splat else "atomic scatter",
+                   "splat": "levels 1-4 gather through vertex -> contributions lists, level 0 atomic scatter" if pipes[0].gather_splat else "atomic scatter",
                    "stem": "conv_in fused into the level-0 splat (input = cloud only)" if stem is not None else "stem features are an input (32 x N f32)",
                    "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                    "algorithmic_MB_per_scan": total_bytes / 1e6,

@@ -115,7 +115,7 @@ class GenerateData(object):
     def _build(self, L, pc1, dev, exact):
         stream = _capi.stream_ptr()
         nlev = len(self.scales_filter_map)
-        states = torch.empty((nlev, STATE_WORDS), dtype=torch.int32, device=dev)
+        states = torch.zeros((nlev, STATE_WORDS), dtype=torch.int32, device=dev)   # (reserved words are never written by the kernels)
         pts = pc1[:3]
         if pts.stride(-1) != 1:
             pts = pts.contiguous()

@@ -1,0 +1,31 @@
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck): two 2048-point scans through one
+batched launch sequence (all lattice kernels, atomic + gather-form splat, tensor-core conv), plus the drop-in
+modules forward + backward on one scan.
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from efgh_b200 import synth
+from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+from efgh_b200.generate_data import GenerateData
+from efgh_b200.bilateralNN import BilateralConvFlex
+
+dev = torch.device("cuda:0")
+n = 2048
+clouds = [synth.synth_scan(s, "os1-64-16k")[:, :n] for s in (0, 1)]
+weights = make_enet_weights(synth.ENET_BCL, seed=1)
+pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=16.0, batch=2)
+feats = torch.randn(32, 2 * n)
+pipe.enqueue(torch.from_numpy(np.concatenate(clouds, 1)).to(dev), feats.to(dev))
+print("batched counts", pipe.counts())
+gd = GenerateData(3, synth.SCALE_MAP[:2], "cuda", exact=False)
+_, data = gd(torch.from_numpy(clouds[0]).to(dev))
+x = torch.randn(1, 32, n, device=dev, requires_grad=True)
+y = x
+for (cin, nout), d in zip(synth.ENET_BCL[:2], data):
+    m = BilateralConvFlex(3, 1, cin, nout, "cuda", True, True, True, True, False, False, chunk_size=-1).to(dev)
+    y = m(torch.cat((d["pc1_el_minus_gr"], y), 1), d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+y.square().mean().backward()
+torch.cuda.synchronize()
+print("modules fwd+bwd ok", float(x.grad.abs().sum()))

@@ -382,6 +382,47 @@ def test_gather_splat_heavy_vertices(batch, dev):
             prev = got_l.double()
 
 
+def test_batched_pipeline_mixed_sensors_fullsize(dev):
+    """BASELINE config 5 clouds in ONE ragged batch: nuScenes-32-like (34 816 pts), OS1-64 (65 536) and HDL-64-like
+    (122 880) scans through one launch sequence; per scan the lattice equals the C oracle bit for bit and the
+    first two BCL levels match the float64 oracle."""
+    from efgh_b200.pipeline import ScanPipeline, make_enet_weights
+    from oracle import lattice as ol, bcl as obcl
+    clouds = [synth.synth_scan(70, "nusc-32"), synth.synth_scan(71, "os1-64-64k"), synth.synth_scan(72, "hdl-64")]
+    sizes = [c.shape[1] for c in clouds]
+    n = max(sizes)
+    B = len(clouds)
+    weights = make_enet_weights(synth.ENET_BCL, seed=8)
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=2.0, batch=B)
+    pipe.set_scan_sizes(sizes)
+    g = torch.Generator().manual_seed(9)
+    feats = [torch.randn(32, sz, generator=g) for sz in sizes]
+    pc_all = torch.zeros(3, B * n)
+    ft_all = torch.zeros(32, B * n)
+    o = 0
+    for b in range(B):
+        pc_all[:, o:o + sizes[b]] = torch.from_numpy(clouds[b])
+        ft_all[:, o:o + sizes[b]] = feats[b]
+        o += sizes[b]
+    pipe.enqueue(pc_all.to(dev), ft_all.to(dev))
+    pipe.counts()
+    for b in range(B):
+        want = ol.generate(clouds[b], synth.SCALE_MAP)
+        got = _to_np(pipe.level_dicts(scan=b))
+        for li, (gl, wl) in enumerate(zip(got, want)):
+            H.assert_level_equal(gl, wl, "mixed batch scan %d L%d" % (b, li))
+        outs = pipe.outputs(scan=b)
+        prev = feats[b][None].double()
+        for li, w in enumerate(want[:2]):
+            ref = obcl.bcl_forward(torch.cat((torch.from_numpy(w["pc1_el_minus_gr"]).double(), prev), 1),
+                                   torch.from_numpy(w["pc1_barycentric"]), torch.from_numpy(w["pc1_lattice_offset"]),
+                                   torch.from_numpy(w["pc1_blur_neighbors"]), weights[li], dtype=torch.float64)
+            got_l = outs[li].cpu()
+            e = H.rel_err(got_l.numpy(), ref.numpy())
+            assert e < PER_LAYER_TOL, "mixed batch scan %d level %d rel err %g" % (b, li, e)
+            prev = got_l.double()
+
+
 # ------------------------------------------------------------------------------------------------
 # wider coverage: BASELINE.json config 5 sweep, slice path, backward at E-Net shapes, radius 2, determinism
 # ------------------------------------------------------------------------------------------------

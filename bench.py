@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--stages", action="store_true", help="print a per-stage timing table to stderr")
     ap.add_argument("--stem", action="store_true",
                     help="SURVEY §8 f1: compute E-Net's pointwise stem inside the level-0 splat; the cloud is then the only input")
+    ap.add_argument("--int32-only", action="store_true",
+                    help="do not write the reference-format int64 copies of lattice_offset / blur_neighbors (the BCL kernels read int32)")
     ap.add_argument("--atomic-splat", action="store_true", help="splat with vector atomics instead of the gather-form splat")
     ap.add_argument("--no-graph", action="store_true", help="enqueue kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -212,7 +214,7 @@ def run_ours(args):
         stem = ([(torch.randn(co, ci, 1, generator=gs_) * 0.3, torch.randn(co, generator=gs_) * 0.1) for ci, co in ((3, 32), (32, 32), (32, 32))], True)
         ft_dev = [None] * NG
     pipes = [ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0, batch=G,
-                          gather_splat=not args.atomic_splat, stem=stem) for _ in range(NP)]
+                          gather_splat=not args.atomic_splat, stem=stem, emit_int64=not args.int32_only) for _ in range(NP)]
     pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0,
                                                  gather_splat=not args.atomic_splat, stem=stem)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
@@ -381,6 +383,7 @@ def run_ours(args):
                                  % (B * total_bytes / 1e6, B, total_bytes / 1e6)),
                    "splat": "levels 1-4 gather through vertex -> contributions lists, level 0 atomic scatter" if pipes[0].gather_splat else "atomic scatter",
                    "stem": "conv_in fused into the level-0 splat (input = cloud only)" if stem is not None else "stem features are an input (32 x N f32)",
+                   "lattice_index_dtype": "int64 (reference format) + int32 copies for the BCL kernels" if pipes[0].emit_int64 else "int32 only",
                    "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                    "algorithmic_MB_per_scan": total_bytes / 1e6,
                    "scan_roofline_frac": total_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},

@@ -191,7 +191,13 @@ __global__ void k_clear(efgh_lattice_state *st, const int32_t *n_dev, int n_host
 
 __device__ __forceinline__ int canonical(int i, int j) { return (j <= 3 - i) ? j : j - 4; }
 
-__global__ void __launch_bounds__(kPointThreads)
+// Minimum CTAs per SM (register caps).  These kernels are latency-bound on random table accesses: k_assign at 83
+// registers ran ONE 512-thread CTA per SM and k_vertices at 78 registers three 256-thread CTAs; capping both at 64
+// registers doubles k_assign's occupancy (measured: lattice stages -6 %); tighter caps spill and lose.
+#ifndef EFGH_LB_POINTS
+#define EFGH_LB_POINTS 4
+#endif
+__global__ void __launch_bounds__(kPointThreads, EFGH_LB_POINTS)
 k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__restrict__ bary,
          float *__restrict__ elmgr, int64_t out_ld, efgh_lattice_state *st, Entry *table_all, int4 *slots, Batch bt) {
   const int n = st->n;
@@ -388,7 +394,10 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
 // order preserved (thread t owns points 2t, 2t+1 of the tile).
 // status word: bits 63..62 = 1 aggregate ready / 2 inclusive prefix ready, low 32 bits = value.
 constexpr int kAssignThreads = kTile / 2;
-__global__ void __launch_bounds__(kAssignThreads)
+#ifndef EFGH_LB_ASSIGN
+#define EFGH_LB_ASSIGN 2
+#endif
+__global__ void __launch_bounds__(kAssignThreads, EFGH_LB_ASSIGN)
 k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
          unsigned long long *__restrict__ vkeys, unsigned long long *tiles, int h_cap, Batch bt) {
   __shared__ int s_tile;
@@ -536,7 +545,10 @@ __device__ __forceinline__ long long floor_mod64(long long a, long long b) {
   return (m != 0 && ((m < 0) != (b < 0))) ? m + b : m;
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef EFGH_LB_VERTICES
+#define EFGH_LB_VERTICES 4
+#endif
+__global__ void __launch_bounds__(256, EFGH_LB_VERTICES)
 k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4 *__restrict__ slots,
            const Entry *__restrict__ table_all, const unsigned long long *__restrict__ vkeys, int64_t *__restrict__ loff, int32_t *__restrict__ loff32,
            int64_t off_ld, const int32_t *__restrict__ foffs, int F, int64_t *__restrict__ nbr,

@@ -292,13 +292,55 @@ k_splat_gather(const float *__restrict__ point_rows, const float *__restrict__ f
     }
   }
 
-  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < H; v += warps) {
-    const int e0 = __ldg(voff + v), e1 = __ldg(voff + v + 1);
-    if (listed && e1 - e0 > kSplatHeavy) continue;        // done above
-    A.clear();
-    for (int base = e0; base < e1; base += 32) A.batch(point_rows, feat2, sn2, C24, contrib, base, e1, lane);
-    A.combine_groups();
-    A.store(S, ldS, v, C24, normalize, inv_out, lane);
+  if constexpr (LPR < 32 && NV == 1) {
+    // Narrow rows (C2 <= 64): one vertex per GROUP of LPR lanes, 32 / LPR vertices per warp side by side.  A lattice
+    // vertex has only 5 - 20 contributions, so a whole warp on one vertex keeps few row reads in flight; with a vertex
+    // per group every lane owns its 4 channels for all contributions (no cross-group reduction) and the warp has
+    // 32 / LPR times as many independent loads outstanding.  Groups diverge freely: the shuffles are group-masked.
+    constexpr int G = 32 / LPR;
+    const int g = lane / LPR, l = lane - g * LPR;
+    const unsigned gmask = ((1u << LPR) - 1u) << (g * LPR);
+    const int n_groups = warps * G;
+    for (int v = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * G + g; v < H; v += n_groups) {
+      const int e0 = __ldg(voff + v), e1 = __ldg(voff + v + 1);
+      if (listed && e1 - e0 > kSplatHeavy) continue;      // done above
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float acc1 = 0.f, wsum = 0.f;
+      for (int base = e0; base < e1; base += LPR) {
+        const bool have = base + l < e1;
+        const int mine = have ? __ldg(contrib + base + l) : 0;
+        const float wmine = have ? __ldg(point_rows + (int64_t)(mine >> 2) * 8 + 4 + (mine & 3)) : 0.f;
+        const int nb = min(LPR, e1 - base);
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) {
+          if (j >= nb) break;                              // group-uniform
+          const int pj = __shfl_sync(gmask, mine, j, LPR);
+          const float wt = __shfl_sync(gmask, wmine, j, LPR);
+          const int i = pj >> 2;
+          if (l < 4) acc1 = fmaf(wt, __ldg(point_rows + (int64_t)i * 8 + l), acc1);
+          wsum += wt;
+          if (l < C24) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(feat2 + (int64_t)i * sn2) + l);
+            acc.x = fmaf(wt, x.x, acc.x); acc.y = fmaf(wt, x.y, acc.y); acc.z = fmaf(wt, x.z, acc.z); acc.w = fmaf(wt, x.w, acc.w);
+          }
+        }
+      }
+      const float inv = __fdiv_rn(1.0f, __fadd_rn(wsum, 1e-5f));
+      const float scl = normalize ? inv : 1.0f;
+      float *out = S + (int64_t)(v + 1) * ldS;
+      if (l < 4) out[l] = acc1 * scl;
+      if (l < C24) *reinterpret_cast<float4 *>(out + 4 + 4 * l) = make_float4(acc.x * scl, acc.y * scl, acc.z * scl, acc.w * scl);
+      if (inv_out && l == 0) inv_out[v + 1] = inv;
+    }
+  } else {
+    for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < H; v += warps) {
+      const int e0 = __ldg(voff + v), e1 = __ldg(voff + v + 1);
+      if (listed && e1 - e0 > kSplatHeavy) continue;        // done above
+      A.clear();
+      for (int base = e0; base < e1; base += 32) A.batch(point_rows, feat2, sn2, C24, contrib, base, e1, lane);
+      A.combine_groups();
+      A.store(S, ldS, v, C24, normalize, inv_out, lane);
+    }
   }
 }
 

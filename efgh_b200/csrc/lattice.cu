@@ -127,13 +127,16 @@ __device__ __forceinline__ void unpack_key(unsigned long long p, int &k0, int &k
   k2 = (int)(p & 0x1fffff) - kBias;
 }
 
+// 32-bit mix of the packed key (murmur3 finaliser over the folded halves): a third of the instructions of a 64-bit
+// finaliser - the lattice kernels execute it 4 times per point and 15 times per vertex.
 __device__ __forceinline__ unsigned hash_key(unsigned long long k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return (unsigned)k;
+  unsigned h = (unsigned)k ^ ((unsigned)(k >> 32) * 0x9e3779b1u);
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
 }
 
 // table size for n points: power of two >= 8n (>= 1024), never above the carved capacity
@@ -609,9 +612,11 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
   const int groups = want_nbr ? 4 : 1;
   const int per_round = blockDim.x / groups;                // vertices per CTA round
   const int g = threadIdx.x / per_round;
+  int scan_end = 0;
   for (int h = blockIdx.x * per_round + (threadIdx.x - g * per_round); h < H; h += gridDim.x * per_round) {
-    if (batched) {                                             // the vertex's own scan: its table, its key box
-      const int scan = find_scan(s_start, bt.B, h);
+    if (batched && h >= scan_end) {                            // the vertex's own scan: its table, its key box
+      const int scan = find_scan(s_start, bt.B, h);              // (h only grows: looked up again when it leaves the scan)
+      scan_end = s_start[scan + 1];
       table = table_all + (long long)scan * bt.tstride;
       mask = (unsigned)bt.info[bt.tm_off + scan];
       const int *box = bt.info + bt.box_off + 8 * scan;

@@ -1,4 +1,5 @@
-"""Debug: timeline of the tensor-core conv roles in CTA 0 (not collected by pytest)."""
+"""(needs a library built with the trace hooks compiled in: make -C efgh_b200/csrc clean all EXTRA=-DEFGH_CONV_TRACE)
+Debug: timeline of the tensor-core conv roles in CTA 0 (not collected by pytest)."""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,7 +40,6 @@ def run(H, C, F, M, label, flags=0, show=0):
         print("%8.2f us  %-4s %d" % (tt / 1000.0, nm, ev))
     print("last event at %.2f us, %d events" % (evs[-1][0] / 1000.0, len(evs)))
 run(100654, 36, 15, 32, "L0 conv1 default", show=150)
-run(100654, 36, 15, 32, "L0 conv1 no-ldgsts", flags=1)
 run(62551, 36, 15, 64, "L1 conv1")
 run(23050, 68, 15, 128, "L2 conv1")
 run(4194, 132, 15, 256, "L3 conv1", show=60)

@@ -60,6 +60,29 @@ def test_pure_host_entry_points(library):
     assert library.efgh_version() >= 100
 
 
+def test_host_side_size_queries():
+    """The batch / gather-splat / stem size queries are pure host arithmetic (no GPU needed)."""
+    L = _capi.lib()
+    assert L.efgh_lattice_table_entries(131072, 4 * 131072) == 1 << 20          # 8 entries per point
+    assert L.efgh_lattice_table_entries(131072, 2 * 131072) == 1 << 19          # sized by the vertex capacity
+    assert L.efgh_lattice_table_entries(1, 1) == 1024                           # floor
+    for B in (1, 2, 16, 64):
+        n = L.efgh_lattice_batch_info_ints(B)
+        assert n >= (B + 1) + B + 8 * B and n % 8 == 0
+    assert L.efgh_lattice_vertex_offsets_ints(1000) > 1001
+    one = L.efgh_lattice_batch_workspace_bytes(1, 1 << 20, 131072)
+    four = L.efgh_lattice_batch_workspace_bytes(4, 1 << 20, 4 * 131072)
+    assert 0 < one < four
+    assert L.efgh_bcl_stem_weight_floats(3, 32, 32, 32) == 3 * 32 + 32 + 2 * (32 * 32 + 32)
+    # tensor-core convolution: shapes of the five E-Net levels are supported, odd shapes are not
+    for cin, (cmid, cout) in ((36, (32, 32)), (36, (64, 64)), (68, (128, 128)), (132, (256, 256)), (260, (256, 256))):
+        assert L.efgh_bcl_conv_tc_supported(cin, 15, cmid, 3) == 1
+        assert L.efgh_bcl_conv_tc_supported(cmid, 1, cout, 3) == 1
+    assert L.efgh_bcl_conv_tc_supported(35, 15, 32, 3) == 0      # C not a multiple of 4
+    assert L.efgh_bcl_conv_tc_supported(36, 15, 48, 3) == 0      # M not a multiple of 32
+    assert L.efgh_bcl_conv_tc_groups(15 * 36) == 3 and L.efgh_bcl_conv_tc_groups(32) == 1
+
+
 def test_no_cpu_fallback():
     """The product modules refuse CPU devices instead of silently computing elsewhere."""
     import torch

@@ -122,6 +122,44 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One K chunk of the 3xTF32 convolution with separate correction accumulators, issued under ONE election: 4 k-steps x
+// [A_big x (B_big | B_small) -> d_main (N' = 2N), A_small x B_big -> d_sb (N)], then the two commits that free the
+// team's A stage and the weight stage.  The MMA issuer's per-chunk instruction chain gates every team's A-stage round
+// trip (a variant with three more uniform-register moves per MMA was measured 5 % slower), so the election, the
+// predicate set-up and the operand increments happen once per chunk, not once per MMA.
+__device__ __forceinline__ void umma_chunk_3x(uint32_t d_main, uint32_t d_sb, uint32_t a_big, uint64_t desc_b, uint32_t idesc2,
+                                               uint32_t idesc, uint32_t acc_main, uint32_t acc_sb, uint32_t bar_a, uint32_t bar_b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pm, ps;\n\t"
+      ".reg .b32 a1, a2, a3, s0, s1, s2, s3;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pm, %6, 0;\n\t"
+      "setp.ne.b32 ps, %7, 0;\n\t"
+      "add.u32 a1, %2, 8;\n\t"
+      "add.u32 a2, %2, 16;\n\t"
+      "add.u32 a3, %2, 24;\n\t"
+      "add.u32 s0, %2, 32;\n\t"
+      "add.u32 s1, %2, 40;\n\t"
+      "add.u32 s2, %2, 48;\n\t"
+      "add.u32 s3, %2, 56;\n\t"
+      "add.u64 b1, %3, 2;\n\t"
+      "add.u64 b2, %3, 4;\n\t"
+      "add.u64 b3, %3, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %4, pm;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [s0], %3, %5, ps;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [s1], b1, %5, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [s2], b2, %5, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], [s3], b3, %5, 1;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+      "}" ::"r"(d_main), "r"(d_sb), "r"(a_big), "l"(desc_b), "r"(idesc2), "r"(idesc), "r"(acc_main), "r"(acc_sb), "r"(bar_a), "r"(bar_b)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -538,11 +576,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           const uint64_t dbb = make_desc(b_big);
           const uint32_t first = j == j_begin;
           if (NSPLIT == 3 && p.nacc >= 2) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc2, !(first && k4 == 0));
-              umma_tf32_ts(d_sb, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0 && p.nacc == 3));
-            }
+            umma_chunk_3x(tmem_d0, d_sb, a_big, dbb, idesc2, idesc, !first, !(first && p.nacc == 3), bar_a_empty + 8 * team,
+                          bar_b_empty + 8 * sb);
           } else if (NSPLIT == 3) {
             const uint64_t dbs = make_desc(b_small);
 #pragma unroll
@@ -555,8 +590,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
           }
-          umma_commit(bar_a_empty + 8 * team);               // frees the team's TMEM A stage when these MMAs retire
-          umma_commit(bar_b_empty + 8 * sb);                 // ... and the weight stage
+          if (!(NSPLIT == 3 && p.nacc >= 2)) {
+            umma_commit(bar_a_empty + 8 * team);             // frees the team's TMEM A stage when these MMAs retire
+            umma_commit(bar_b_empty + 8 * sb);               // ... and the weight stage
+          }
           if (lane == 0) trace_ev(p.trace, 3, ntrace, 3);
           pha_bits ^= 1u << team;
           if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1; }

@@ -575,7 +575,11 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
   if (loff || loff32) {
     for (int i = tid; i < n; i += stride) {
       const int4 s = slots[i];
-      const int v0 = table_all[s.x].index, v1 = table_all[s.y].index, v2 = table_all[s.z].index, v3 = table_all[s.w].index;
+      int v0 = table_all[s.x].index, v1 = table_all[s.y].index, v2 = table_all[s.z].index, v3 = table_all[s.w].index;
+      // More vertices than the caller's capacity (EFGH_ST_VERTEX_CAP is set, the level's results are void): indices
+      // beyond the capacity become -2 so that no consumer - the splat adds 1 and skips negative rows - ever leaves
+      // the vertex-side arrays.
+      v0 = v0 < h_cap ? v0 : -2; v1 = v1 < h_cap ? v1 : -2; v2 = v2 < h_cap ? v2 : -2; v3 = v3 < h_cap ? v3 : -2;
       if (loff) {
         long long *lo = reinterpret_cast<long long *>(loff);
         __stcs(lo + i, (long long)v0); __stcs(lo + off_ld + i, (long long)v1);
@@ -588,7 +592,7 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
         const int v[4] = {v0, v1, v2, v3};
         int pos[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) pos[r] = v[r] < h_cap ? atomicAdd(&bt.cursor[v[r]], 1) : -1;
+        for (int r = 0; r < 4; ++r) pos[r] = v[r] >= 0 ? atomicAdd(&bt.cursor[v[r]], 1) : -1;
 #pragma unroll
         for (int r = 0; r < 4; ++r) if (pos[r] >= 0) bt.contrib[pos[r]] = 4 * i + r;
       }
@@ -677,7 +681,7 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
             cur = ((unsigned long long)(unsigned)e2.y << 32) | (unsigned)e2.x;
             idx = e2.w;
           }
-          res[t] = cur == want[t] ? idx : -1;
+          res[t] = (cur == want[t] && idx < h_cap) ? idx : -1;   // (idx >= h_cap only when the vertex capacity overflowed)
           if (ali[t] && res[t] >= 0) aliased = true;           // an out-of-box key aliased onto an existing vertex:
                                                                // the neighbour table loses its mirror symmetry
         }

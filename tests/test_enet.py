@@ -83,3 +83,40 @@ def test_enet_forward_backward_step():
     assert float(model.bcn1.blur_conv[0].weight.grad.abs().max()) > 0     # gradient reached the first BCL through 5 levels
     opt.step()
     assert not torch.equal(before, model.bcn3.blur_conv[0].weight.detach())
+
+
+@pytest.mark.gpu
+def test_enet_batched_inference_matches_module_path():
+    """Enet.infer (one batched ScanPipeline launch sequence: stem fused into the level-0 splat, gather-form splat, no
+    host sync per level) returns what forward() returns cloud by cloud: BCL features within the chained tolerance,
+    same gravity-normal estimate.  Weights are re-drawn (the reference's N(0, 1e-3) init gives ~0 features)."""
+    from efgh_b200.enet import Enet
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = Enet(ARGS).to(dev).eval()
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.startswith(("conv_in", "bcn")):
+                p.normal_(0, 0.1 if p.dim() > 1 else 0.05)
+    clouds = [torch.from_numpy(synth.synth_scan(80 + b, "os1-64-16k")).to(dev) for b in range(3)]
+    # the module path's stem is a cuDNN Conv1d, which torch lets run in TF32 by default (1e-3 off); the fused stem is fp32
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    request_restore = tf32
+    with torch.no_grad():
+        want = [net(c[None]) for c in clouds]
+        got = net.infer(clouds, vertex_cap_factor=0.5)          # too small on purpose: exercises the capacity retry
+    for b in range(3):
+        for li, (g, w) in enumerate(zip(got[b]["bcn_outputs"], want[b]["bcn_outputs"])):
+            assert tuple(g.shape) == tuple(w.shape)
+            err = float((g - w).abs().max() / w.abs().max())
+            assert err < 5e-5, "cloud %d level %d rel err %g" % (b, li, err)
+        assert float((got[b]["e_gn"] - want[b]["e_gn"]).abs().max()) < 1e-4
+    # weights changed in place -> the cached pipeline must be rebuilt
+    with torch.no_grad():
+        net.bcn1.blur_conv[0].weight.mul_(2.0)
+        want2 = net(clouds[0][None])
+        got2 = net.infer(clouds[:1])
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = request_restore
+    err = float((got2[0]["bcn_outputs"][0] - want2["bcn_outputs"][0]).abs().max() / want2["bcn_outputs"][0].abs().max())
+    assert err < 5e-5, "after an in-place weight update: rel err %g" % err

@@ -29,3 +29,14 @@ for (cin, nout), d in zip(synth.ENET_BCL[:2], data):
 y.square().mean().backward()
 torch.cuda.synchronize()
 print("modules fwd+bwd ok", float(x.grad.abs().sum()))
+
+# capacity overflow: more vertices than the arrays hold -> status bit, no out-of-bounds access
+from efgh_b200.generate_data import VertexCapExceeded
+small = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=0.5, batch=2)
+small.enqueue(torch.from_numpy(np.concatenate(clouds, 1)).to(dev), feats.to(dev))
+try:
+    small.counts()
+    print("unexpected: no overflow")
+except VertexCapExceeded as e:
+    print("overflow reported:", e)
+torch.cuda.synchronize()

@@ -52,7 +52,9 @@ constexpr int kTeams = 4;                    // producer teams; team t converts 
 constexpr int kProducerWarps = 4 * kTeams;
 constexpr int kMmaWarp = kProducerWarps, kTmaWarp = kProducerWarps + 1, kEpiWarp0 = kProducerWarps + 2;
 constexpr int kThreads = (kEpiWarp0 + 4) * 32;  // 704
-constexpr int kMaxRaw = 3;                   // raw-row slots per producer warp
+constexpr int kMaxRaw = 1;                   // raw-row slots per producer warp.  One: with 16 producer warps per SM the copy latency is
+                                             // hidden by the other warps, deeper rings were measured no faster inside the kernel, and the
+                                             // 64-128 KB of shared memory they cost made the whole launch sequence 3.6 % slower
 constexpr int kRawSlotBytes = kTeams * kTileM * 128;  // one raw slot for all teams (512 threads x 128 B)
 constexpr int kEpiRowFloats = 36;            // padded row of the epilogue staging tile (bank-conflict free)
 constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;

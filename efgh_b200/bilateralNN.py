@@ -6,9 +6,11 @@ load with strict=True (reference main.py:136) and reference nets/enet.py:30-141 
 
 What differs underneath: splat is one vector-atomic scatter into a vertex-major
 matrix instead of two sparse COO coalesces of a (4N, C) temporary; the (1, C, F, H) gathered tensor
-is never materialised - neighbour rows are read straight into the convolution's shared-memory tile;
-the density normalisation is folded into that read.  Forward and backward both run through the C ABI
-in include/efgh_b200.h; there is no PyTorch fallback.
+is never materialised - neighbour rows are copied straight into the tensor-core convolution's operand
+pipeline; the density normalisation is one in-place pass over the splat matrix.  Forward and backward both
+run through the C ABI in include/efgh_b200.h (the data gradient as a gather-form convolution on the same
+tensor-core kernel); there is no PyTorch fallback.  (Whole scans / batches without per-call overheads:
+efgh_b200.pipeline.ScanPipeline.)
 
 Only batch size 1 is meaningful in the reference (bilateralNN.py:162-165: "batch size can only be 1
 for now"; the splat indices carry no batch offset), so B != 1 raises here instead of silently mixing

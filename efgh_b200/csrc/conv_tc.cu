@@ -40,7 +40,12 @@ static unsigned long long *g_conv_trace = nullptr;
 // Debug hook (not part of the public header): device buffer of 5 roles x 512 x 2 u64 that CTA 0 fills with
 // (event, globaltimer) pairs, or NULL to disable.
 extern "C" void efgh_debug_set_conv_trace(unsigned long long *buf) { g_conv_trace = buf; }
-static int g_conv_flags = 0;   // debug: bit0 = skip the gather copies (wrong results, timing only); bits 4-7 = raw-slot override
+// Debug / timing-study switches (tools/conv_tc_time.py, tools/tf32_truncation_probe.py; not part of the public header):
+//   bit 1        publish a converted chunk after the next copy issue instead of at once
+//   bit 2        one-pass TF32 only: hand the tensor core unmasked fp32 A
+//   bits 4-7     cap on raw-row slots      bits 8-13   chunks per K group
+//   bits 16-23   producers' poll sleep / 8 ns (0xff = none)      bits 24-31   relaxed waits' sleep / 8 ns
+static int g_conv_flags = 0;
 extern "C" void efgh_debug_set_conv_flags(int flags) { g_conv_flags = flags; }
 
 namespace efgh {

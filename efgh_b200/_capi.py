@@ -17,6 +17,7 @@ SIGNATURES = {
     "efgh_last_error": (ctypes.c_char_p, []),
     "efgh_version": (i32, []),
     "efgh_device_sm_count": (i32, []),
+    "efgh_launch_count": (i64, []),
     "efgh_copy_matrix_async": (i32, [vp, i64, vp, i64, i64, i64, i32, vp]),
     "efgh_lattice_workspace_bytes": (sz, [i64]),
     "efgh_lattice_points": (i32, [vp, i64, i64, vp, f32, vp, vp, i64, i64, vp, vp, sz, vp]),

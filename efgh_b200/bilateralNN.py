@@ -17,6 +17,7 @@ for now"; the splat indices carry no batch offset), so B != 1 raises here instea
 the batch entries.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -45,6 +46,7 @@ def init_weights(m):
         m.weight.data.normal_(0, 1e-3)
         if m.bias is not None:
             m.bias.data.zero_()
+        invalidate_weight_cache(m.weight)                # `.data` edits do not bump the parameter's version
     elif isinstance(m, nn.BatchNorm2d):
         m.weight.data.fill_(1)
         m.bias.data.zero_()
@@ -117,7 +119,8 @@ def conv(X, nbr, Wt, bias, act, h, wkey=None):
         F, bits, nbp, nb_ld = 1, 64, None, 0
     L = _capi.lib()
     nsplit = _NSPLIT.get(CONV_PRECISION, 0)
-    if nsplit and L.efgh_bcl_conv_tc_supported(C, F, M, nsplit) and X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0:
+    if (nsplit and L.efgh_bcl_conv_tc_supported(C, F, M, nsplit) and X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0
+            and (bias is None or bias.data_ptr() % 16 == 0)):
         K = Wt.shape[0]
         img = _cached("img", wkey if wkey is not None else Wt, nsplit, lambda: _tc_image(Wt, nsplit))
         split = L.efgh_bcl_conv_tc_groups(K) > 1        # long contraction: partial sums are added in L2
@@ -258,18 +261,38 @@ def conv_wgrad(X, row_scale, nbr, dY, act_out, act, want_bias):
     return dWt, db
 
 
-# Re-laid weights ((K, M) matrices and the tensor-core kernel's packed images) are cached ON the parameter object, per
-# parameter VERSION: torch bumps `_version` on every in-place update (optimizer step, load_state_dict), so inference
-# re-uses them call after call, training rebuilds them once per step, and the cache dies with the parameter.
+# Re-laid weights ((K, M) matrices and the tensor-core kernel's packed images) are cached per parameter OBJECT in a
+# module-level table (not on the parameter: attributes of a Parameter travel with torch.save(model)).  An entry is
+# valid while (version, storage address, device, dtype) are unchanged: torch bumps `_version` on every in-place update
+# through the tensor itself (optimizer step, load_state_dict, copy_), and `.to(device)` / `.half()` change the address.
+# Edits through `.data` (init_weights below, the reference's initialisers, EMA / clipping code) change none of those,
+# so (a) a forward that autograd records - training - drops its parameters' entries first (BilateralConvFlex.forward):
+# re-laying the weights once per step is small next to the convolution; (b) init_weights invalidates explicitly;
+# (c) callers that edit `.data` at inference time call invalidate_weight_cache() (BilateralConvFlex.invalidate_cache()).
+_WEIGHT_CACHE = {}      # id(parameter) -> (weakref, state key, {(kind, extra): tensor})
+
+
+def invalidate_weight_cache(*params):
+    """Drop the cached re-laid / packed weights of `params` (all parameters when called without arguments)."""
+    if not params:
+        _WEIGHT_CACHE.clear()
+        return
+    for p in params:
+        _WEIGHT_CACHE.pop(id(p), None)
+
+
 def _cached(kind, W, extra, build):
-    cache = getattr(W, "_efgh_cache", None)
-    if cache is None or cache[0] != W._version:
-        cache = (W._version, {})
+    state = (W._version, W.data_ptr(), W.device, W.dtype)
+    ent = _WEIGHT_CACHE.get(id(W))
+    if ent is None or ent[0]() is not W or ent[1] != state:
+        wid = id(W)
         try:
-            W._efgh_cache = cache
-        except Exception:       # not an attribute-carrying tensor: just rebuild every call
+            ref = weakref.ref(W, lambda _r, wid=wid: _WEIGHT_CACHE.pop(wid, None))
+        except TypeError:                                # not weak-referenceable: just rebuild every call
             return build()
-    d = cache[1]
+        ent = (ref, state, {})
+        _WEIGHT_CACHE[wid] = ent
+    d = ent[2]
     key = (kind, extra)
     if key not in d:
         d[key] = build()
@@ -457,6 +480,10 @@ class BilateralConvFlex(nn.Module):
     def get_filter_size(self):
         return (self.neighborhood_size + 1) ** self.d1 - self.neighborhood_size ** self.d1
 
+    def invalidate_cache(self):
+        """Call after editing weights through `.data` under no_grad (those edits are invisible to the version counter)."""
+        invalidate_weight_cache(*[p for p in self.parameters()])
+
     def forward(self, features,
                 in_barycentric, in_lattice_offset,
                 blur_neighbors,
@@ -474,6 +501,8 @@ class BilateralConvFlex(nn.Module):
             if isinstance(m, nn.Conv2d):
                 wb += [m.weight, m.bias]
         slice_bias = self.bias if (self.do_slice and self.use_bias) else None
+        if torch.is_grad_enabled() and any(p.requires_grad for p in wb):
+            invalidate_weight_cache(*wb)                 # training: weights change between calls, possibly through `.data`
         return _BCLFunction.apply(cfg, features, in_barycentric, in_lattice_offset, blur_neighbors,
                                   out_barycentric if self.do_slice else None,
                                   out_lattice_offset if self.do_slice else None, slice_bias, *wb)

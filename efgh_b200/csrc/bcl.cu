@@ -945,19 +945,18 @@ extern "C" int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *ro
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dispatch_idx(idx_bits, [&](auto tag) -> int {
     using IdxT = decltype(tag);
-    if (M <= 32) {
-      constexpr int BM = 128, BN = 32;
+    // dynamic shared memory: the tile's neighbour rows, F x BM ints - beyond 48 KB the kernel attribute must be raised
+    auto launch = [&](auto kern, int BM, int BN) -> int {
+      const size_t smem = sizeof(int) * (size_t)F * BM;
+      EFGH_REQUIRE(smem <= 160 * 1024, "efgh_bcl_conv: filter size %d too large for the fp32 kernel (row table %zu bytes)", F, smem);
+      if (smem > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid(grid_for((h + BM - 1) / BM, 1, 4), (M + BN - 1) / BN);
-      k_conv<IdxT, BM, BN, 4, 4><<<grid, 256, sizeof(int) * F * BM, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev,
-                                                                         Wt, bias, M, act, Y, ldY);
-    } else {
-      constexpr int BM = 64, BN = 64;
-      dim3 grid(grid_for((h + BM - 1) / BM, 1, 4), (M + BN - 1) / BN);
-      k_conv<IdxT, BM, BN, 4, 4><<<grid, 256, sizeof(int) * F * BM, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev,
-                                                                         Wt, bias, M, act, Y, ldY);
-    }
-    EFGH_LAUNCH_CHECK();
-    return EFGH_OK;
+      kern<<<grid, 256, smem, s>>>(X, ldX, C, row_scale, nbr, nbr_ld, F, (int)h, h_dev, Wt, bias, M, act, Y, ldY);
+      EFGH_LAUNCH_CHECK();
+      return EFGH_OK;
+    };
+    if (M <= 32) return launch(k_conv<IdxT, 128, 32, 4, 4>, 128, 32);
+    return launch(k_conv<IdxT, 64, 64, 4, 4>, 64, 64);
   });
 }
 

@@ -14,6 +14,10 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static thread_local int cached[64] = {0};
   int dev = 0;
@@ -29,7 +33,9 @@ int sm_count() {
 }  // namespace efgh
 
 extern "C" const char *efgh_last_error(void) { return efgh::g_error; }
-extern "C" int efgh_version(void) { return 100; }
+extern "C" int efgh_version(void) { return 200; }
+namespace efgh { unsigned long long launches(); }
+extern "C" int64_t efgh_launch_count(void) { return (int64_t)efgh::launches(); }
 extern "C" int efgh_device_sm_count(void) {
   int dev = 0, v = 0;
   cudaError_t e = cudaGetDevice(&dev);

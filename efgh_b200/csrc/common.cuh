@@ -11,6 +11,7 @@ namespace efgh {
 
 void set_error(const char *fmt, ...);
 int sm_count();
+void note_launch();   // bumps the process-wide kernel-launch counter (efgh_launch_count)
 
 // Turns a CUDA error into the C-ABI status code + message.
 #define EFGH_CUDA_CHECK(expr)                                                                   \
@@ -30,7 +31,11 @@ int sm_count();
     }                                 \
   } while (0)
 
-#define EFGH_LAUNCH_CHECK() EFGH_CUDA_CHECK(cudaGetLastError())
+#define EFGH_LAUNCH_CHECK()              \
+  do {                                   \
+    efgh::note_launch();                 \
+    EFGH_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
 
 // Grid for a grid-stride kernel over `items` work items: enough CTAs to cover the items once, capped at
 // a multiple of the SM count (148 on B200) so that a capacity-sized launch does not flood the machine

@@ -543,11 +543,6 @@ __device__ __forceinline__ int table_find(const Entry *__restrict__ table, unsig
   return -1;
 }
 
-__device__ __forceinline__ long long floor_mod64(long long a, long long b) {
-  long long m = a % b;
-  return (m != 0 && ((m < 0) != (b < 0))) ? m + b : m;
-}
-
 #ifndef EFGH_LB_VERTICES
 #define EFGH_LB_VERTICES 4
 #endif
@@ -627,12 +622,18 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
 #pragma unroll
       for (int c = 0; c < 4; ++c) { kmin[c] = box[c]; kmax[c] = box[4 + c]; }
     }
-    const long long s1 = (long long)kmax[1] - kmin[1] + 1, s2 = (long long)kmax[2] - kmin[2] + 1,
-                    s3 = (long long)kmax[3] - kmin[3] + 1, s0 = (long long)kmax[0] - kmin[0] + 1;
+    // Spans of the key box.  The reference packs keys with int64 arithmetic that wraps (numba, transforms.py:62-78);
+    // unsigned arithmetic reproduces the wrap without undefined behaviour.  A box so wide that the in-box packing
+    // itself overflows 2^63 (spans of ~55 000 in every coordinate - far outside any LiDAR cloud) is flagged.
+    const unsigned long long s1 = (unsigned long long)((long long)kmax[1] - kmin[1] + 1), s2 = (unsigned long long)((long long)kmax[2] - kmin[2] + 1),
+                             s3 = (unsigned long long)((long long)kmax[3] - kmin[3] + 1), s0 = (unsigned long long)((long long)kmax[0] - kmin[0] + 1);
+    const unsigned long long s01 = s0 * s1, s23 = s2 * s3;            // each span < 2^22: the pair products are exact
+    const bool box_ok = __umul64hi(s01, s23) == 0 && (long long)(s01 * s23) >= 0;
+    const unsigned long long box = s01 * s23;
     int k[4];
     unpack_key(vkeys[h], k[0], k[1], k[2]);
     k[3] = -(k[0] + k[1] + k[2]);
-    bool aliased = false;
+    bool aliased = false, wide_box = false;
     if (want_nbr) {
       for (int f0 = g; f0 < F; f0 += 16) {
         unsigned long long want[4];
@@ -652,12 +653,13 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
           if (!in_box) {
             // transforms.py:62-78: the reference looks the neighbour up by its mixed-radix packed integer,
             // which can alias a DIFFERENT in-box key when the neighbour lies outside the key box.
-            long long P = (((long long)(q[0] - kmin[0]) * s1 + (q[1] - kmin[1])) * s2 + (q[2] - kmin[2])) * s3 +
-                          (q[3] - kmin[3]);
-            if (!(P >= 0 && P < s0 * s1 * s2 * s3)) continue;
-            const long long a3 = floor_mod64(P, s3); P = (P - a3) / s3;
-            const long long a2 = floor_mod64(P, s2); P = (P - a2) / s2;
-            const long long a1 = floor_mod64(P, s1); P = (P - a1) / s1;
+            if (!box_ok) { wide_box = true; continue; }
+            unsigned long long P = ((((unsigned long long)(long long)(q[0] - kmin[0])) * s1 + (unsigned long long)(long long)(q[1] - kmin[1])) * s2 +
+                                    (unsigned long long)(long long)(q[2] - kmin[2])) * s3 + (unsigned long long)(long long)(q[3] - kmin[3]);
+            if (!(P < box)) continue;                          // (as int64: negative or beyond every stored key)
+            const unsigned long long a3 = P % s3; P /= s3;      // int2key (transforms.py:81-92) on a non-negative value
+            const unsigned long long a2 = P % s2; P /= s2;
+            const unsigned long long a1 = P % s1; P /= s1;
             q[0] = (int)P + kmin[0]; q[1] = (int)a1 + kmin[1]; q[2] = (int)a2 + kmin[2]; q[3] = (int)a3 + kmin[3];
             ali[t] = true;
           }
@@ -695,6 +697,7 @@ k_vertices(efgh_lattice_state *__restrict__ st, int n_cap, int h_cap, const int4
       }
     }
     if (aliased) atomicOr(&st->status, EFGH_ST_ALIASED);
+    if (wide_box) atomicOr(&st->status, EFGH_ST_KEY_RANGE);
     if (next_pts && g == 0) {                                // generate_data.py:177-178
       float q[4];
 #pragma unroll

@@ -138,10 +138,14 @@ class Enet(nn.Module):
         from .pipeline import ScanPipeline
         bcns = (self.bcn1, self.bcn2, self.bcn3, self.bcn4, self.bcn5)
         params = [p for m in (self.conv_in,) + bcns for p in m.parameters()]
-        key = (n_points, batch, vertex_cap_factor, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
-        cached = getattr(self, "_fast", None)
-        if cached is not None and cached[0] == key:
-            return cached[1]
+        wkey = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        cache = getattr(self, "_fast", None)
+        if cache is None or cache["wkey"] != wkey:              # weights changed: every cached pipeline holds stale copies
+            cache = {"wkey": wkey, "pipes": {}, "factor": {}}
+            self._fast = cache
+        key = (n_points, batch, vertex_cap_factor)
+        if key in cache["pipes"]:
+            return cache["pipes"][key]
         gd = self.generate_data
         plan, weights = [], []
         for m in bcns:
@@ -155,33 +159,46 @@ class Enet(nn.Module):
         pipe = ScanPipeline(n_points, gd.scales_filter_map, plan, weights, dev, stem_channels=plan[0][0] - 4,
                             vertex_cap_factor=vertex_cap_factor, emit_int64=False, last_relu=self.bcn1.last_relu,
                             use_leaky=self.bcn1.use_leaky, use_norm=self.bcn1.use_norm, batch=batch, stem=stem)
-        self._fast = (key, pipe)
+        if len(cache["pipes"]) >= 4:                            # a few shapes at most: each pipeline owns all its buffers
+            cache["pipes"].pop(next(iter(cache["pipes"])))
+        cache["pipes"][key] = pipe
         return pipe
 
     @torch.no_grad()
     def infer(self, clouds, vertex_cap_factor=2.0):
         """clouds: list of (3, N) CUDA tensors with the same N (or one (B, 3, N) tensor).  Returns one forward()-style
         dict per cloud.  The lattice + BCL part runs as ONE batched launch sequence; if a level overflows its vertex
-        capacity the pipeline is rebuilt with twice the capacity and the batch is run again."""
-        from .generate_data import VertexCapExceeded
+        capacity (or its hash table) the batch is run again through a pipeline with twice the capacity, and that
+        capacity is remembered for the next call with the same (N, B).  `bcn_outputs` are copies: the pipeline's own
+        buffers are overwritten by the next infer()."""
+        from .generate_data import VertexCapExceeded, LatticeStatusError
         if torch.is_tensor(clouds):
             clouds = list(clouds)
         B, n = len(clouds), clouds[0].shape[-1]
         assert all(c.shape[-1] == n and c.is_cuda for c in clouds)
-        pc_all = torch.cat([c[:3].float() for c in clouds], dim=1).contiguous()
-        while True:
-            pipe = self._pipeline(n, B, vertex_cap_factor)
-            pipe.enqueue(pc_all, None)
-            try:
-                starts = pipe.vertex_starts() if B > 1 else None
-                pipe.counts()
-                break
-            except VertexCapExceeded:
-                vertex_cap_factor *= 2.0
-        outs = []
-        for b in range(B):
-            bcn = pipe.outputs(scan=b) if B > 1 else pipe.outputs()
-            outs.append(self._head(bcn[-1], bcn))
+        dev = next(self.parameters()).device
+        with torch.cuda.device(dev):
+            pc_all = torch.cat([c[:3].float() for c in clouds], dim=1).contiguous()
+            self._pipeline(n, B, vertex_cap_factor)             # (validates / resets the weight key of the cache)
+            factor = max(vertex_cap_factor, self._fast["factor"].get((n, B), 0.0))
+            while True:
+                pipe = self._pipeline(n, B, factor)
+                pipe.enqueue(pc_all, None)
+                try:
+                    starts = pipe.vertex_starts() if B > 1 else None
+                    pipe.counts()
+                    break
+                except VertexCapExceeded:
+                    pass
+                except LatticeStatusError as e:
+                    if "hash table full" not in str(e) or factor > 256 * vertex_cap_factor:
+                        raise
+                factor *= 2.0
+            self._fast["factor"][(n, B)] = factor
+            outs = []
+            for b in range(B):
+                bcn = [o.clone() for o in (pipe.outputs(scan=b) if B > 1 else pipe.outputs())]
+                outs.append(self._head(bcn[-1], bcn))
         return outs
 
     def _head(self, out, bcn_outs):

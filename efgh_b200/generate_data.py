@@ -81,7 +81,7 @@ class GenerateData(object):
         self._offsets_dev = {}
         for radius in set(item for line in scales_filter_map for item in line[1:] if item != -1):
             self.radius2offset[radius] = blur_offsets(radius, self.d0)
-        self._workspace = None
+        self._workspace = {}          # per (device, stream): instances may be shared by concurrent streams
         self.last_states = None
 
     def get_filter_size(self, radius):
@@ -96,9 +96,14 @@ class GenerateData(object):
 
     def _ws(self, n_cap, device):
         need = _capi.lib().efgh_lattice_workspace_bytes(int(n_cap))
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._workspace
+        key = (device, _capi.stream_ptr())
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < need:
+            if len(self._workspace) >= 8:
+                self._workspace.clear()
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._workspace[key] = ws
+        return ws
 
     def __call__(self, pc1):
         L = _capi.lib()

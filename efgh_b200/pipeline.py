@@ -22,6 +22,8 @@ streams are concatenated, every scan keeps its own hash table / key box / insert
 The ~55 launches and, more importantly, the latency-bound small kernels of the coarse levels (a few thousand
 vertices each) are paid once per batch instead of once per scan.
 """
+import functools
+
 import numpy as np
 import torch
 
@@ -29,6 +31,15 @@ from . import _capi
 from .generate_data import GenerateData, STATE_WORDS, check_status, VertexCapExceeded
 
 _ACT = {"none": 0, "relu": 1, "leaky": 2}
+
+
+def _on_own_device(fn):
+    """The C ABI launches on the CURRENT CUDA device; streams and buffers belong to self.dev."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class ScanPipeline(object):
@@ -52,6 +63,7 @@ class ScanPipeline(object):
         self.B = int(batch)
         assert 1 <= self.B <= 64
         self.gather_splat = bool(gather_splat)
+        self.level0_splat = "vector-atomic scatter + normalise"
         self.stem = None
         if stem is not None:
             layers, leaky = stem
@@ -152,6 +164,7 @@ class ScanPipeline(object):
         # per launch sequence: clear/points/assign, vertices, zero, splat (+ normalise | level-0 transpose), conv1, conv2
         self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 2) + sum(0 if lv["gs"] else 1 for lv in self.levels)
 
+    @_on_own_device
     def set_scan_sizes(self, sizes):
         """Batched pipelines: ragged batch - scan b has sizes[b] (1 <= sizes[b] <= n_points) points, stored back to
         back in the (3, B*n_points) / (C, B*n_points) inputs.  Synchronising (rewrites a device array that enqueued
@@ -165,6 +178,7 @@ class ScanPipeline(object):
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------
+    @_on_own_device
     def enqueue(self, pc, feat0, stream=None, timers=None):
         """pc (3,N) f32, feat0 (C_stem,N) f32 device tensors.  Enqueues the whole scan on `stream` (default:
         current).  Returns the last level's output buffer Z (h_cap, C_out) - valid rows = states[-1, 1].
@@ -296,6 +310,7 @@ class ScanPipeline(object):
             n_dev = h_dev
         return self.levels[-1]["Z"]
 
+    @_on_own_device
     def graph_for(self, pc, feat0, stream):
         """CUDA graph of enqueue(pc, feat0) (captured once per input-buffer pair, then replayed): the ~55 launches
         of a scan become one graph launch, which removes the per-launch host cost and most inter-kernel gaps."""
@@ -310,6 +325,7 @@ class ScanPipeline(object):
             self._graphs[key] = g
         return g
 
+    @_on_own_device
     def forward_host(self, pc_host, feat_host, out_host, state_host, stream=None, use_graph=False, starts_host=None,
                      compute_stream=None):
         """End-to-end call on HOST buffers (pinned for async copies): H2D of the cloud and stem features,

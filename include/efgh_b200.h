@@ -65,6 +65,9 @@ const char *efgh_last_error(void);
 int efgh_version(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int efgh_device_sm_count(void);
+/* kernels launched by this library in this process so far (bench.py's `gpu_launches` is a difference of two reads;
+ * launches replayed from a captured CUDA graph are not re-counted) */
+int64_t efgh_launch_count(void);
 
 /* Strided host <-> device copy of a (rows, cols) float32 matrix (leading dimensions in elements);
  * kind 1 = host -> device, 2 = device -> host.  Packs one scan's (3,n) / (C,n) host matrix into its column

@@ -16,13 +16,31 @@ import subprocess
 import sys
 import types
 
-REF_ROOT = os.environ.get("EFGH_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_OUT = os.path.join(HERE, "_ref")
+# Where the unmodified reference files are: the build container's /root/reference, else the git-ignored install
+# baseline/_ref/ that baseline/install_ref.py copied from it (that copy travels to the GPU box; bench.py's
+# `--impl reference` arm is its only user there).
+INSTALLED = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("EFGH_REFERENCE"), "/root/reference", INSTALLED):
+        if cand and os.path.isfile(os.path.join(cand, "nets", "generate_data.py")):
+            return cand
+    return os.environ.get("EFGH_REFERENCE", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available():
     return os.path.isfile(os.path.join(REF_ROOT, "nets", "generate_data.py"))
+
+
+def is_live():
+    """True when the files come from the read-only reference checkout itself (build container)."""
+    return available() and os.path.realpath(REF_ROOT) != os.path.realpath(INSTALLED)
 
 
 def build_khash_ffi():
@@ -31,6 +49,12 @@ def build_khash_ffi():
     built = [f for f in os.listdir(REF_OUT) if f.startswith("_khash_ffi") and f.endswith(".so")]
     if built:
         return
+    inst = os.path.join(INSTALLED, "lib")
+    if os.path.isdir(inst):                                  # built by baseline/install_ref.py
+        for f in os.listdir(inst):
+            if f.startswith("_khash_ffi") and f.endswith(".so"):
+                shutil.copy(os.path.join(inst, f), REF_OUT)
+                return
     tmp = os.path.join(REF_OUT, "_cffi_build")
     os.makedirs(tmp, exist_ok=True)
     for f in ("khash.h", "khash_int2int.h", "build_khash_cffi.py"):

@@ -1,0 +1,170 @@
+"""GPU (-m gpu): BCL backward at every E-Net shape against the float64 oracle's autograd, and the
+NCCL gradient all-reduce of the training configuration (BASELINE configs[3])."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from efgh_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 2e-5          # max abs error / max abs value of the float64 oracle gradient
+CHAIN_GRAD_TOL = 1e-4    # five chained layers: per-layer forward errors compound into the gradients
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from efgh_b200 import _capi
+    _capi.lib()
+    return torch.device("cuda:0")
+
+
+_lattices = {}
+
+
+def _lattice(sensor, dev):
+    """Five-level lattice of one synthetic cloud (built once per module): the real neighbour tables / offsets every
+    level's BCL sees in E-Net."""
+    if sensor not in _lattices:
+        from efgh_b200.generate_data import GenerateData
+        pc = synth.synth_scan(11, sensor)
+        gd = GenerateData(3, synth.SCALE_MAP, "cuda", exact=True)
+        _, data = gd(torch.from_numpy(pc).to(dev))
+        _lattices[sensor] = data
+    return _lattices[sensor]
+
+
+def _module(level, dev, seed):
+    from efgh_b200.bilateralNN import BilateralConvFlex
+    cin, nout = synth.ENET_BCL[level]
+    torch.manual_seed(seed)
+    m = BilateralConvFlex(3, 1, cin, list(nout), "cuda", True, True, True, True, False, False, chunk_size=-1).to(dev)
+    for p in m.parameters():
+        torch.nn.init.normal_(p, 0, 0.1)
+    return m
+
+
+def _oracle_grads(m, d, feat, gout):
+    from oracle import bcl as obcl
+    convs = [(c.weight.detach().cpu().double().requires_grad_(True), c.bias.detach().cpu().double().requires_grad_(True))
+             for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    f = feat.detach().cpu().double().requires_grad_(True)
+    out = obcl.bcl_forward(f, d["pc1_barycentric"].cpu(), d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs,
+                           dtype=torch.float64)
+    out.backward(gout.double())
+    return out.detach(), f.grad, convs
+
+
+@pytest.mark.parametrize("sensor", ["os1-64-16k", "os1-64-64k"])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
+def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch):
+    """Every E-Net BCL shape (36->[32,32] ... 260->[256,256]) on its REAL lattice level of a 16k and a 65k cloud:
+    forward within 1e-5 and d features / d weights / d biases within 2e-5 of the float64 oracle's autograd - for the
+    tensor-core (gather-form) and the scatter-form data gradient, with int64 and int32 lattice indices."""
+    from efgh_b200 import bilateralNN
+    d = _lattice(sensor, dev)[level]
+    cin, nout = synth.ENET_BCL[level]
+    n_in = d["pc1_barycentric"].shape[-1]
+    m = _module(level, dev, 20 + level)
+    g = torch.Generator().manual_seed(100 + level)
+    feat0 = torch.randn(1, cin, n_in, generator=g)
+    gout = torch.randn(1, nout[-1], d["pc1_hash_cnt"], generator=g)
+    ref_out, ref_gfeat, ref_convs = _oracle_grads(m, d, feat0, gout)
+    mods = [c for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    for dgrad_tc in (True, False):
+        for idx_dtype in ((torch.int64, torch.int32) if dgrad_tc else (torch.int64,)):
+            monkeypatch.setattr(bilateralNN, "DGRAD_ON_TENSOR_CORES", dgrad_tc)
+            m.zero_grad(set_to_none=True)
+            feat = feat0.to(dev).requires_grad_(True)
+            off = d["pc1_lattice_offset"].to(idx_dtype)
+            nbr = d["pc1_blur_neighbors"].to(idx_dtype)
+            out = m(feat, d["pc1_barycentric"], off, nbr, None, None)
+            ctx = "level %d %s dgrad=%s idx=%s" % (level, sensor, "tc" if dgrad_tc else "scatter", idx_dtype)
+            assert H.rel_err(out.detach().cpu().numpy(), ref_out.numpy()) < 1e-5, ctx
+            out.backward(gout.to(dev))
+            assert H.rel_err(feat.grad.cpu().numpy(), ref_gfeat.numpy()) < GRAD_TOL, ctx + " d feat"
+            for c, (W, b) in zip(mods, ref_convs):
+                assert H.rel_err(c.weight.grad.cpu().numpy(), W.grad.numpy()) < GRAD_TOL, ctx + " d weight"
+                assert H.rel_err(c.bias.grad.cpu().numpy(), b.grad.numpy()) < GRAD_TOL, ctx + " d bias"
+
+
+def test_bcl_chain_backward_vs_oracle_chain(dev):
+    """The five E-Net BCLs chained as reference nets/enet.py:113-141 (level l's input = cat(el_minus_gr_l, level l-1's
+    output)), loss on bcn5's output: gradients of the stem features and of all 20 weight / bias tensors against the
+    float64 oracle chain's autograd."""
+    from oracle import bcl as obcl
+    data = _lattice("os1-64-16k", dev)
+    mods = [_module(li, dev, 40 + li) for li in range(5)]
+    g = torch.Generator().manual_seed(7)
+    feat0 = torch.randn(1, 32, data[0]["pc1_barycentric"].shape[-1], generator=g)
+    gout = torch.randn(1, 256, data[4]["pc1_hash_cnt"], generator=g)
+    x = feat0.to(dev).requires_grad_(True)
+    h = x
+    for d, m in zip(data, mods):
+        h = m(torch.cat((d["pc1_el_minus_gr"], h), 1), d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+    h.backward(gout.to(dev))
+    f = feat0.double().requires_grad_(True)
+    ref_w = []
+    r = f
+    for d, m in zip(data, mods):
+        convs = [(c.weight.detach().cpu().double().requires_grad_(True), c.bias.detach().cpu().double().requires_grad_(True))
+                 for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+        ref_w.append(convs)
+        r = obcl.bcl_forward(torch.cat((d["pc1_el_minus_gr"].cpu().double(), r), 1), d["pc1_barycentric"].cpu(),
+                             d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs, dtype=torch.float64)
+    r.backward(gout.double())
+    assert H.rel_err(h.detach().cpu().numpy(), r.detach().numpy()) < 5e-5
+    assert H.rel_err(x.grad.cpu().numpy(), f.grad.numpy()) < CHAIN_GRAD_TOL, "d stem features"
+    for li, (m, convs) in enumerate(zip(mods, ref_w)):
+        cs = [c for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+        for c, (W, b) in zip(cs, convs):
+            assert H.rel_err(c.weight.grad.cpu().numpy(), W.grad.numpy()) < CHAIN_GRAD_TOL, "level %d d weight" % li
+            assert H.rel_err(c.bias.grad.cpu().numpy(), b.grad.numpy()) < CHAIN_GRAD_TOL, "level %d d bias" % li
+
+
+def test_weight_cache_sees_data_edits_and_device_moves(dev):
+    """re-laid / packed weights must never go stale - not after `.data` edits recorded by autograd-less
+    code paths (explicit invalidation), not after an optimizer step, not across `init_weights`."""
+    from efgh_b200 import bilateralNN
+    d = _lattice("os1-64-16k", dev)[0]
+    m = _module(0, dev, 3)
+    feat = torch.randn(1, 36, d["pc1_barycentric"].shape[-1], device=dev)
+    args = (d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+    with torch.no_grad():
+        y0 = m(feat, *args).clone()
+        assert torch.equal(m(feat, *args), y0)                      # cached path, same result
+        m.blur_conv[0].weight.mul_(2.0)                              # in-place through the tensor: version bump
+        y1 = m(feat, *args).clone()
+        assert not torch.allclose(y1, y0)
+        m.blur_conv[0].weight.data.mul_(0.5)                         # through .data: invisible to the version counter
+        m.invalidate_cache()
+        assert H.rel_err(m(feat, *args).cpu().numpy(), y0.cpu().numpy()) < 1e-6
+    # training: a recorded forward never trusts the cache
+    m.blur_conv[0].weight.data.mul_(2.0)
+    y2 = m(feat.requires_grad_(True), *args)
+    assert H.rel_err(y2.detach().cpu().numpy(), y1.cpu().numpy()) < 1e-6
+    for mod in m.blur_conv.modules():
+        bilateralNN.init_weights(mod)
+    with torch.no_grad():
+        assert float(m(feat, *args).abs().max()) < 1e-3              # N(0, 1e-3) weights: the old images are gone
+
+
+@pytest.mark.parametrize("world", [2])
+def test_gradient_allreduce_nccl(world, dev):
+    """sharding.allreduce_gradients over NCCL (one process per GPU, torchrun): replicas with different per-rank
+    gradients end up with the mean on every rank, in a few bucketed calls."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tests", "nccl_allreduce_worker.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "NCCL_ALLREDUCE_OK" in r.stdout, r.stdout[-2000:]

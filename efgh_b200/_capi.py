@@ -39,7 +39,7 @@ SIGNATURES = {
     "efgh_bcl_conv_tc_supported": (i32, [i32, i32, i32, i32]),
     "efgh_bcl_packed_weight_bytes": (sz, [i32, i32, i32]),
     "efgh_bcl_pack_weights": (i32, [vp, i32, i32, i32, vp, vp]),
-    "efgh_bcl_conv_tc_groups": (i32, [i32]),
+    "efgh_bcl_conv_tc_groups": (i32, [i32, i32]),
     "efgh_bcl_conv_tc": (i32, [vp, i64, i32, vp, i32, vp, i32, i64, i32, i64, vp, vp, vp, i32, i32, vp, i64, i32, i32, vp]),
     "efgh_bcl_normalize": (i32, [vp, i64, i32, vp, vp, i64, vp, i32, vp]),
     "efgh_bcl_bias_act": (i32, [vp, i64, i32, i64, vp, vp, i32, vp]),

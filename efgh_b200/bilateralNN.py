@@ -26,6 +26,9 @@ from . import _capi
 from .generate_data import blur_offsets
 
 DELETE_TMP_VARIABLES = False
+# Test hook: when set to a dict, every forward stores its convolutions' activations (post-ReLU, vertex-major) under "ys" -
+# the backward parity tests need the ReLU active set the kernels actually used (tests/test_gpu_backward.py).
+DEBUG_KEEP = None
 
 _ACT = {"none": 0, "relu": 1, "leaky": 2}
 
@@ -123,7 +126,7 @@ def conv(X, nbr, Wt, bias, act, h, wkey=None):
             and (bias is None or bias.data_ptr() % 16 == 0)):
         K = Wt.shape[0]
         img = _cached("img", wkey if wkey is not None else Wt, nsplit, lambda: _tc_image(Wt, nsplit))
-        split = L.efgh_bcl_conv_tc_groups(K) > 1        # long contraction: partial sums are added in L2
+        split = L.efgh_bcl_conv_tc_groups(K, M) > 1     # wide output + long contraction: partial sums are added in L2
         if split:
             Y.zero_()
         _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), X.stride(0), C, None, 0, nbp, bits, nb_ld, F, h,
@@ -207,7 +210,7 @@ def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit, symmetric=None
         if not dYm.is_contiguous():
             dYm = dYm.contiguous()
         img = _tc_image(W[:, :, 0, 0].contiguous(), nsplit)          # (K = M_k, C)
-        split = L.efgh_bcl_conv_tc_groups(Mk) > 1
+        split = L.efgh_bcl_conv_tc_groups(Mk, C) > 1
         dX = (torch.zeros if split else torch.empty)((h, C), dtype=torch.float32, device=dY.device)
         _capi.check(L.efgh_bcl_conv_tc(dYm.data_ptr(), Mk, Mk, None, 0, None, 64, 0, 1, h, None, img.data_ptr(), None, C,
                                        0, dX.data_ptr(), C, nsplit, 1 if split else 0, _capi.stream_ptr()),
@@ -229,7 +232,7 @@ def conv_dgrad_tc(dY, act_out, act, nbr, W, mirror, rows, nsplit, symmetric=None
     Wg = W[:, rem:, :, 0][:, :, list(mirror)].permute(2, 0, 1).reshape(F * Mk, Cg).contiguous()
     img = _tc_image(Wg, nsplit)
     dX = torch.zeros((rows, C), dtype=torch.float32, device=dY.device)
-    split = L.efgh_bcl_conv_tc_groups(F * Mk) > 1
+    split = L.efgh_bcl_conv_tc_groups(F * Mk, Cg) > 1
     out = dX[1:, rem:]
     _capi.check(L.efgh_bcl_conv_tc(Xp.data_ptr(), Mk, Mk, None, 0, nb2.data_ptr(), _idx_bits(nb2), nb_ld, F, h, None,
                                    img.data_ptr(), None, Cg, 0, out.data_ptr(), C, nsplit, 1 if split else 0,
@@ -341,6 +344,8 @@ class _BCLFunction(torch.autograd.Function):
                 Y = conv(X, nb, Wt, b, act, H, wkey=W)
                 xs.append(X); ys.append(Y); wts.append(Wt); acts.append(act)
                 X, nb = Y, None
+            if DEBUG_KEEP is not None:
+                DEBUG_KEEP["ys"] = ys
             if do_slice:
                 n_out = out_bary.shape[-1]
                 out = gather(X, None, out_bary, out_off, 0, slice_bias, n_out)[None]

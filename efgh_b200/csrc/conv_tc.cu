@@ -28,10 +28,16 @@
 //               row stores, or red.add.v4 of the raw partial sum into Y (split-K / chain cut, see below).
 //
 // Tensor-core accumulation rounds toward zero, so the error of a long accumulation chain grows linearly
-// with its length; chains are cut every kGroupChunks chunks and the partial sums are added in L2 with
-// round-to-nearest atomics.  The same cut is the split-K that keeps all 148 SMs busy on the small
-// lattices of the deep levels.  Work item = (128-vertex tile, K group); persistent CTAs, one per SM,
-// stride over the items; the vertex count is read from device memory.
+// with its length; chains are CUT every kGroupChunks chunks and the partial sums are added with
+// round-to-nearest adds.  Two ways, chosen by the output width:
+//   N <= 128  on chip: a work item is a whole 128-vertex tile; the epilogue warps drain every cut's accumulator
+//             (the other accumulator stage is being filled meanwhile) into a running sum held in shared memory -
+//             the same tile that transposes the result for coalesced stores - and write Y ONCE, with bias and
+//             activation applied.  No atomics, no zero-fill of Y, no deferred bias;
+//   N == 256  (no room for a 128 KB running sum next to the weight stages) in L2: work item = (tile, K group),
+//             partial sums added with red.add.v4 into a zero-filled Y, bias + activation deferred to the consumer.
+//             The same split keeps all 148 SMs busy on the small lattices of the deep levels.
+// Persistent CTAs, one per SM, stride over the items; the vertex count is read from device memory.
 //
 // TMEM map (512 columns): [accumulators: acc_stages x nacc x N] [A operand: 4 teams x (32 big | 32 small)].
 #include "common.cuh"
@@ -62,7 +68,6 @@ constexpr int kMaxRaw = 1;                   // raw-row slots per producer warp.
                                              // 64-128 KB of shared memory they cost made the whole launch sequence 3.6 % slower
 constexpr int kRawSlotBytes = kTeams * kTileM * 128;  // one raw slot for all teams (512 threads x 128 B)
 constexpr int kEpiRowFloats = 36;            // padded row of the epilogue staging tile (bank-conflict free)
-constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;
 constexpr int kBiasFloats = 256 + 512;       // output bias (N <= 256) + input bias (C <= 512) staged in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -258,6 +263,7 @@ struct ConvParams {
   const float *Wimg; const float *bias; int N; int act;
   float *Y; int64_t ldY;
   int n_chunks; int n_groups;
+  int cut_chunks;                       // > 0: on-chip chain cuts - an item's chunks are accumulated in runs of <= cut_chunks, summed by the epilogue
   int b_stages, raw_slots, acc_stages, nacc;   // nacc: independent accumulators per stage (see the MMA issuer)
   uint32_t magic_c;                     // ceil(2^32 / C): k / C == __umulhi(k, magic_c) for the k range used here
   int accumulate;                       // 1: red.add raw partial sums into pre-zeroed Y (bias/act deferred); 0: store act(bias + acc)
@@ -313,8 +319,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   const int N = p.N;
   const uint32_t b_bytes = (uint32_t)N * 128u * (NSPLIT == 3 ? 2 : 1);
   const uint32_t raw_base = smem_base + (uint32_t)p.b_stages * b_bytes;
-  const uint32_t epi_base = raw_base + (uint32_t)p.raw_slots * kRawSlotBytes;   // 4 epilogue warps x 32 rows x 36 floats
-  float *s_bias = reinterpret_cast<float *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes + kEpiStageBytes);
+  const uint32_t epi_base = raw_base + (uint32_t)p.raw_slots * kRawSlotBytes;   // 4 epilogue warps x 32 rows x epi_pitch floats
+  const int epi_pitch = p.cut_chunks > 0 ? N + 4 : kEpiRowFloats;               // on-chip cuts: the whole 128 x N running sum lives here
+  float *s_bias = reinterpret_cast<float *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes + (size_t)(4 * 32 * 4) * epi_pitch);
   float *s_in_bias = s_bias + 256;
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + kBiasFloats);
   // barrier map (8 B each): A_full[4 teams] A_empty[4] (2 spare each) B_full[4] B_empty[4] acc_full[2] acc_empty[2]
@@ -551,11 +558,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       // uniform datapath instead of costing an R2UR per operand per MMA
       const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
       const uint32_t idesc = make_idesc(N);
-      uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0, seq = 0;
+      uint32_t tcount = 0, sb = 0, phb = 0, pha_bits = 0, seq = 0;   // tcount: accumulator hand-overs (one per cut)
       int ntrace = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int gi = item % p.n_groups;
-        const int j_begin = s_gb[gi], j_end = s_gb[gi + 1];
+        const int i_begin = s_gb[gi], i_end = s_gb[gi + 1];
+        const int n_cut = p.cut_chunks > 0 ? max(1, (i_end - i_begin + p.cut_chunks - 1) / p.cut_chunks) : 1;
+        for (int c = 0; c < n_cut; ++c, ++tcount) {
+        int j_begin, j_end;
+        group_range(i_end - i_begin, n_cut, c, j_begin, j_end);
+        j_begin += i_begin; j_end += i_begin;
         const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
         const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
         if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
@@ -606,6 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           if (++sb == (uint32_t)p.b_stages) { sb = 0; phb ^= 1; }
         }
         umma_commit(bar_acc_full + 8 * as);                  // accumulator complete -> epilogue
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -614,19 +627,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     uint32_t tcount = 0;
     int ntrace = 0;
     const bool tracer = threadIdx.x == kEpiWarp0 * 32;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
-      const int tile = item / p.n_groups;
+    const uint32_t pitch_b = (uint32_t)epi_pitch * 4u;                       // bytes per staged row
+    const uint32_t stage = epi_base + (uint32_t)(warp - kEpiWarp0) * (32u * pitch_b);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item / p.n_groups, gi = item - tile * p.n_groups;
+      const int n_cut = p.cut_chunks > 0 ? max(1, (s_gb[gi + 1] - s_gb[gi] + p.cut_chunks - 1) / p.cut_chunks) : 1;
+      const int h_warp = tile * kTileM + q * 32;
+      for (int c = 0; c < n_cut; ++c, ++tcount) {
       const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
       const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+      const bool last = c == n_cut - 1;
       if (tracer) trace_ev(p.trace, 4, ntrace, 100 + (int)tcount);
       mbar_wait_relaxed(bar_acc_full + 8 * as, aph, relax_ns);
       tc_fence_after();
       if (tracer) trace_ev(p.trace, 4, ntrace, 1);
-      // Each thread holds 32 consecutive columns of ITS row after tcgen05.ld; going straight to global memory
-      // would touch 32 rows x 16 B per instruction.  Stage the 32x32 block through shared memory so that every
-      // store / reduction instruction covers 4 rows x 128 contiguous bytes (8 lanes per row).
-      const uint32_t stage = epi_base + (uint32_t)(warp - kEpiWarp0) * (32 * kEpiRowFloats * 4);
-      const int h_warp = tile * kTileM + q * 32;
+      // Each thread holds 32 consecutive columns of ITS row after tcgen05.ld.  The 32 x N block of this warp is staged
+      // in shared memory, row = lane: (a) cuts of a long contraction are summed there with round-to-nearest adds
+      // (every thread touches only its own row: no synchronisation until the last cut), (b) the last cut reads it back
+      // transposed so that every global store / reduction instruction covers 4 rows x 128 contiguous bytes.
       for (int cb = 0; cb < N; cb += 32) {
         float v[32];
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(p.nacc * N) + cb;
@@ -638,23 +656,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
         if (tracer) trace_ev(p.trace, 4, ntrace, 10);
+        const uint32_t my_row = stage + (uint32_t)lane * pitch_b + (p.cut_chunks > 0 ? (uint32_t)cb * 4u : 0u);
+        if (c > 0) {                                          // running sum of the earlier cuts of this tile
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 r;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(my_row + (uint32_t)u * 16u));
+            v[4 * u] += r.x; v[4 * u + 1] += r.y; v[4 * u + 2] += r.z; v[4 * u + 3] += r.w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)u * 16u),
+                       "f"(v[4 * u]), "f"(v[4 * u + 1]), "f"(v[4 * u + 2]), "f"(v[4 * u + 3])
+                       : "memory");
+        if (!last) continue;
         // bias of the 4 columns this lane will store after the transposition (one 16-byte load per block)
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!p.accumulate) bv = *(reinterpret_cast<const float4 *>(s_bias + cb) + (lane & 7));
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * (kEpiRowFloats * 4) + (uint32_t)u * 16u),
-                       "f"(v[4 * u]), "f"(v[4 * u + 1]), "f"(v[4 * u + 2]), "f"(v[4 * u + 3])
-                       : "memory");
         __syncwarp();
         if (tracer) trace_ev(p.trace, 4, ntrace, 11);
         float4 o[8];
+        const uint32_t blk = stage + (p.cut_chunks > 0 ? (uint32_t)cb * 4u : 0u);
 #pragma unroll
         for (int it8 = 0; it8 < 8; ++it8) {                   // all shared loads first, then all global stores: one warp cannot hide
           const int row = it8 * 4 + (lane >> 3);              // the load latency of an interleaved load/store sequence
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(o[it8].x), "=f"(o[it8].y), "=f"(o[it8].z), "=f"(o[it8].w)
-                       : "r"(stage + (uint32_t)row * (kEpiRowFloats * 4) + (uint32_t)(lane & 7) * 16u));
+                       : "r"(blk + (uint32_t)row * pitch_b + (uint32_t)(lane & 7) * 16u));
         }
         float *ybase = p.Y + (int64_t)(h_warp + (lane >> 3)) * p.ldY + cb + 4 * (lane & 7);
         const int h_lane = h_warp + (lane >> 3);
@@ -683,13 +712,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           for (int it8 = 0; it8 < 8; ++it8)
             if (h_lane + 4 * it8 < H) *reinterpret_cast<float4 *>(ybase + (int64_t)(4 * it8) * p.ldY) = o[it8];
         }
-        __syncwarp();
+        __syncwarp();                                         // (without on-chip cuts the next block re-uses this staging tile)
         if (tracer) trace_ev(p.trace, 4, ntrace, 12);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
       if (tracer) trace_ev(p.trace, 4, ntrace, 2);
+      }
     }
   }
 
@@ -747,8 +777,11 @@ extern "C" int efgh_bcl_bias_act(float *Y, int64_t ldY, int M, int64_t h, const 
   return EFGH_OK;
 }
 
+// Output widths up to this keep the running sum of an item's chain cuts in shared memory (128 rows x N floats).
+constexpr int kOnChipMaxN = 128;
+
 // Resource plan for output width N: TMEM = acc_stages*N + 4 teams x (32|64) A columns <= 512;
-// shared memory = b_stages weight tiles + raw_slots x 64 KB of warp-private row slots.
+// shared memory = b_stages weight tiles + raw_slots x 64 KB of warp-private row slots + the epilogue tile.
 static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   const int a_cols = nsplit == 3 ? 64 : 32;
   const int room = 512 - kTeams * a_cols;                // TMEM columns left for accumulators
@@ -760,13 +793,15 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   else if (2 * N <= room) { nacc = 1; acc_stages = 2; }
   if (acc_stages * nacc * N > room) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
-  const size_t budget = 224 * 1024 - 1024 - 256 - (kMaxGroups + 4) * 4 - kProducerWarps * 256 - kEpiStageBytes - kBiasFloats * 4;
+  const size_t epi_bytes = (size_t)4 * 32 * 4 * (N <= kOnChipMaxN ? N + 4 : kEpiRowFloats);
+  const size_t fixed = 1024 + 256 + (kMaxGroups + 4) * 4 + kProducerWarps * 256 + epi_bytes + kBiasFloats * 4;
+  const size_t budget = 226 * 1024 - fixed;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
   int raw = (int)((budget - (size_t)b_stages * b_bytes) / kRawSlotBytes);
   if (raw > kMaxRaw) raw = kMaxRaw;
   if (p) { p->b_stages = b_stages; p->raw_slots = raw; p->acc_stages = acc_stages; p->nacc = nacc; }
-  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + kEpiStageBytes + kBiasFloats * 4 + 256 + (kMaxGroups + 4) * 4 + kProducerWarps * 256 + 1024;
+  if (smem_out) *smem_out = (size_t)b_stages * b_bytes + (size_t)raw * kRawSlotBytes + fixed;
   return true;
 }
 
@@ -790,12 +825,14 @@ extern "C" int efgh_bcl_pack_weights(const float *Wt, int K, int M, int nsplit, 
   return EFGH_OK;
 }
 
-// Number of K groups (= partial sums per output) the kernel will use for a contraction of length K.  The
-// tensor core accumulates in TMEM with round-toward-zero, so its error grows linearly with the length of
-// an accumulation chain; chains are cut every kGroupChunks x 32 terms and the partial sums are added in L2
-// (red.add.f32, round-to-nearest).  The same cut is the split-K that keeps all SMs busy on small lattices.
+// Number of partial sums per output that the kernel adds IN GLOBAL MEMORY for a contraction of length K and output
+// width M.  The tensor core accumulates in TMEM with round-toward-zero, so its error grows linearly with the length
+// of an accumulation chain; chains are cut every kGroupChunks x 32 terms.  For M <= 128 the cuts are summed on chip
+// (returns 1: Y is written once, bias and activation applied); for wider outputs they are K groups added in L2
+// (red.add.f32 into a zero-filled Y; the same split keeps all SMs busy on small lattices).
 constexpr int kGroupChunks = 8;
-extern "C" int efgh_bcl_conv_tc_groups(int K) {
+extern "C" int efgh_bcl_conv_tc_groups(int K, int M) {
+  if (M <= kOnChipMaxN) return 1;
   const int chunks = (K + kChunkK - 1) / kChunkK;
   return (chunks + kGroupChunks - 1) / kGroupChunks;
 }
@@ -820,7 +857,12 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   p.h_host = (int)h; p.h_dev = h_dev; p.Wimg = Wimg; p.bias = bias; p.N = M; p.act = act; p.Y = Y; p.ldY = ldY;
   p.in_bias = in_bias; p.in_act = in_act; p.accumulate = accumulate;
   p.n_chunks = (F * C + kChunkK - 1) / kChunkK;
-  p.n_groups = efgh_bcl_conv_tc_groups(F * C);
+  p.n_groups = efgh_bcl_conv_tc_groups(F * C, M);
+  p.cut_chunks = M <= kOnChipMaxN ? kGroupChunks : 0;
+  if ((g_conv_flags >> 8) & 63) {                            // timing studies: chunks per chain
+    if (p.cut_chunks) p.cut_chunks = (g_conv_flags >> 8) & 63;
+    else p.n_groups = (p.n_chunks + ((g_conv_flags >> 8) & 63) - 1) / ((g_conv_flags >> 8) & 63);
+  }
   p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
   EFGH_REQUIRE(p.n_groups <= kMaxGroups, "efgh_bcl_conv_tc: K=%d too long (%d K groups, at most %d)", F * C, p.n_groups, kMaxGroups);
   EFGH_REQUIRE(accumulate || p.n_groups == 1,

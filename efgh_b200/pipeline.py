@@ -140,14 +140,14 @@ class ScanPipeline(object):
                 lv["b1"] = b1.detach().to(dev, f32).contiguous()
                 lv["tc"] = bool(self.nsplit and self.L.efgh_bcl_conv_tc_supported(cin, F, cmid, self.nsplit)
                                 and self.L.efgh_bcl_conv_tc_supported(cmid, 1, cout, self.nsplit)
-                                and self.L.efgh_bcl_conv_tc_groups(cmid) == 1)
+                                and self.L.efgh_bcl_conv_tc_groups(cmid, cout) == 1)
                 if lv["tc"]:
                     for nm, K, M in (("img0", F * cin, cmid), ("img1", cmid, cout)):
                         img = torch.empty(self.L.efgh_bcl_packed_weight_bytes(K, M, self.nsplit) // 4, dtype=f32, device=dev)
                         _capi.check(self.L.efgh_bcl_pack_weights(lv["Wt" + nm[-1]].data_ptr(), K, M, self.nsplit, img.data_ptr(),
                                                                  torch.cuda.current_stream(dev).cuda_stream), "efgh_bcl_pack_weights")
                         lv[nm] = img
-                    lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin) > 1
+                    lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin, cmid) > 1
                 if self.batch_api:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, lv["table"], n_cap))
                 else:

@@ -245,16 +245,17 @@ int efgh_bcl_conv(const float *X, int64_t ldX, int C, const float *row_scale, co
  * row_scale argument: normalise the splat matrix first (efgh_bcl_normalize) - rows are copied from L2 into
  * the tensor core's shared-memory tiles asynchronously, without passing through registers.
  *
- * Long contractions are cut into efgh_bcl_conv_tc_groups(K) partial sums (tensor-core accumulation rounds
- * toward zero, so chains are kept short; the cut is also the split-K that fills the GPU on small lattices).
- *   accumulate = 0: Y = act(bias + sum); only valid when efgh_bcl_conv_tc_groups(F*C) == 1;
- *   accumulate = 1: Y += partial sums (red.add in L2) - the caller zero-fills Y first; bias/act are NOT
- *                   applied: finish with efgh_bcl_bias_act, or let the consumer apply them on load through
- *                   its in_bias / in_act arguments.
- *   in_bias (C floats) / in_act: optional transform of the INPUT, x = act(x + in_bias[c]), applied as rows are
- *                   gathered - the deferred bias + ReLU of a producer that ran with accumulate = 1. */
+ * Long contractions are cut into chains of 256 terms (tensor-core accumulation rounds toward zero, so a chain's error
+ * grows with its length) whose partial sums are added with round-to-nearest adds:
+ *   M <= 128: on chip (shared-memory running sum in the epilogue); efgh_bcl_conv_tc_groups(K, M) == 1 and
+ *             accumulate = 0 writes Y = act(bias + sum) once;
+ *   M  > 128: efgh_bcl_conv_tc_groups(K, M) K groups added in L2 (also the split-K that fills the SMs on small
+ *             lattices): call with accumulate = 1 on a zero-filled Y - the kernel then adds raw partial sums and the
+ *             caller applies bias / activation afterwards (efgh_bcl_bias_act, or `in_bias` / `in_act` of the next
+ *             efgh_bcl_conv_tc, which applies act(x + in_bias[c]) to X while loading it).
+ * accumulate = 0 is only valid when efgh_bcl_conv_tc_groups(F*C, M) == 1. */
 int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit);
-int efgh_bcl_conv_tc_groups(int K);
+int efgh_bcl_conv_tc_groups(int K, int M);
 size_t efgh_bcl_packed_weight_bytes(int K, int M, int nsplit);
 int efgh_bcl_pack_weights(const float *Wt, int K, int M, int nsplit, float *Wimg, void *stream);
 int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float *in_bias, int in_act,

@@ -11,10 +11,16 @@ import torch
 
 def bcl_forward(features, in_bary, in_off, nbrs, convs, *, use_norm=True, do_splat=True,
                 do_slice=False, out_bary=None, out_off=None, slice_bias=None,
-                last_relu=False, use_leaky=True, dtype=None):
+                last_relu=False, use_leaky=True, dtype=None, relu_masks=None, pre_acts=None):
     """features (1,C_in,N) | (1,C_in,H) if not do_splat; in_bary (1,4,N); in_off (1,4,N) int64;
     nbrs (1,F,H) int64 with -1 = absent; convs = [(W0 (C1,C_in,F,1), b0), (W1 (C2,C1,1,1), b1), ...].
-    Returns (1,C_out,H), or (1,C_out,N_out) when slicing."""
+    Returns (1,C_out,H), or (1,C_out,N_out) when slicing.
+
+    Test hooks (not part of the reference): `pre_acts`, a list that receives the pre-activation (H, C) of every
+    inter-convolution ReLU; `relu_masks`, a list of (H, C) bool tensors used INSTEAD of `y > 0` - a ReLU's
+    derivative is discontinuous at 0, so a backward comparison must run both sides with the same active set
+    (the tests assert that the two active sets differ only where the pre-activation is within the forward tolerance
+    of zero)."""
     dt = dtype or features.dtype
     feat = features[0].to(dt)                       # (C,N)
     nb = nbrs[0]                                    # (F,H)
@@ -34,7 +40,9 @@ def bcl_forward(features, in_bary, in_off, nbrs, convs, *, use_norm=True, do_spl
     W0, b0 = convs[0]
     y = torch.einsum("fhc,mcf->hm", X, W0[..., 0].to(dt)) + b0.to(dt)   # Conv2d (F,1) :244
     for li, (Wk, bk) in enumerate(convs[1:]):       # ReLU between convs, :111-115
-        y = torch.relu(y)
+        if pre_acts is not None:
+            pre_acts.append(y.detach())
+        y = torch.relu(y) if relu_masks is None else y * relu_masks[li].to(dt)
         y = y @ Wk[:, :, 0, 0].to(dt).t() + bk.to(dt)
     if last_relu:                                   # :121-134
         y = torch.nn.functional.leaky_relu(y, 0.1) if use_leaky else torch.relu(y)

@@ -80,7 +80,8 @@ def test_host_side_size_queries():
         assert L.efgh_bcl_conv_tc_supported(cmid, 1, cout, 3) == 1
     assert L.efgh_bcl_conv_tc_supported(35, 15, 32, 3) == 0      # C not a multiple of 4
     assert L.efgh_bcl_conv_tc_supported(36, 15, 48, 3) == 0      # M not a multiple of 32
-    assert L.efgh_bcl_conv_tc_groups(15 * 36) == 3 and L.efgh_bcl_conv_tc_groups(32) == 1
+    assert L.efgh_bcl_conv_tc_groups(15 * 36, 32) == 1 and L.efgh_bcl_conv_tc_groups(15 * 132, 128) == 1     # cuts summed on chip
+    assert L.efgh_bcl_conv_tc_groups(15 * 132, 256) == 8 and L.efgh_bcl_conv_tc_groups(256, 256) == 1        # K groups added in L2
 
 
 def test_no_cpu_fallback():

@@ -51,13 +51,38 @@ def _module(level, dev, seed):
     return m
 
 
-def _oracle_grads(m, d, feat, gout):
+def _oracle_convs(m):
+    return [(c.weight.detach().cpu().double().requires_grad_(True), c.bias.detach().cpu().double().requires_grad_(True))
+            for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+
+
+def _oracle_pre(m, d, feat):
+    """Forward only: output and the pre-activation of the ReLU between the two convolutions."""
     from oracle import bcl as obcl
-    convs = [(c.weight.detach().cpu().double().requires_grad_(True), c.bias.detach().cpu().double().requires_grad_(True))
-             for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    pre = []
+    with torch.no_grad():
+        out = obcl.bcl_forward(feat.detach().cpu().double(), d["pc1_barycentric"].cpu(), d["pc1_lattice_offset"].cpu(),
+                               d["pc1_blur_neighbors"].cpu(), _oracle_convs(m), dtype=torch.float64, pre_acts=pre)
+    return out, pre[0]
+
+
+def _check_active_set(mask_gpu, pre, tol, ctx):
+    """A ReLU's derivative jumps at 0: the kernels' active set may differ from the float64 oracle's only where the
+    oracle's pre-activation lies within the FORWARD tolerance of zero.  Returns the number of such elements."""
+    differ = mask_gpu != (pre > 0)
+    n = int(differ.sum())
+    if n:
+        worst = float(pre[differ].abs().max() / pre.abs().max())
+        assert worst < tol, "%s: ReLU active sets differ at a pre-activation %.2e of the maximum away from zero" % (ctx, worst)
+    return n
+
+
+def _oracle_grads(m, d, feat, gout, mask):
+    from oracle import bcl as obcl
+    convs = _oracle_convs(m)
     f = feat.detach().cpu().double().requires_grad_(True)
     out = obcl.bcl_forward(f, d["pc1_barycentric"].cpu(), d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs,
-                           dtype=torch.float64)
+                           dtype=torch.float64, relu_masks=[mask])
     out.backward(gout.double())
     return out.detach(), f.grad, convs
 
@@ -67,7 +92,9 @@ def _oracle_grads(m, d, feat, gout):
 def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch):
     """Every E-Net BCL shape (36->[32,32] ... 260->[256,256]) on its REAL lattice level of a 16k and a 65k cloud:
     forward within 1e-5 and d features / d weights / d biases within 2e-5 of the float64 oracle's autograd - for the
-    tensor-core (gather-form) and the scatter-form data gradient, with int64 and int32 lattice indices."""
+    tensor-core (gather-form) and the scatter-form data gradient, with int64 and int32 lattice indices.  Both sides
+    differentiate the inner ReLU with the kernels' active set, after checking that it differs from the oracle's own
+    only at pre-activations within the forward tolerance of zero (_check_active_set)."""
     from efgh_b200 import bilateralNN
     d = _lattice(sensor, dev)[level]
     cin, nout = synth.ENET_BCL[level]
@@ -76,8 +103,10 @@ def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch
     g = torch.Generator().manual_seed(100 + level)
     feat0 = torch.randn(1, cin, n_in, generator=g)
     gout = torch.randn(1, nout[-1], d["pc1_hash_cnt"], generator=g)
-    ref_out, ref_gfeat, ref_convs = _oracle_grads(m, d, feat0, gout)
+    ref_out, pre = _oracle_pre(m, d, feat0)
     mods = [c for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    keep = {}
+    monkeypatch.setattr(bilateralNN, "DEBUG_KEEP", keep)
     for dgrad_tc in (True, False):
         for idx_dtype in ((torch.int64, torch.int32) if dgrad_tc else (torch.int64,)):
             monkeypatch.setattr(bilateralNN, "DGRAD_ON_TENSOR_CORES", dgrad_tc)
@@ -88,37 +117,50 @@ def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch
             out = m(feat, d["pc1_barycentric"], off, nbr, None, None)
             ctx = "level %d %s dgrad=%s idx=%s" % (level, sensor, "tc" if dgrad_tc else "scatter", idx_dtype)
             assert H.rel_err(out.detach().cpu().numpy(), ref_out.numpy()) < 1e-5, ctx
+            mask = (keep["ys"][0] > 0).cpu()                      # the active set of the ReLU the kernels applied
+            flips = _check_active_set(mask, pre, 1e-5, ctx)
+            _, ref_gfeat, ref_convs = _oracle_grads(m, d, feat0, gout, mask)
             out.backward(gout.to(dev))
+            print("%s: %d ReLU elements within the forward tolerance of 0 differ from the oracle's active set" % (ctx, flips))
             assert H.rel_err(feat.grad.cpu().numpy(), ref_gfeat.numpy()) < GRAD_TOL, ctx + " d feat"
             for c, (W, b) in zip(mods, ref_convs):
                 assert H.rel_err(c.weight.grad.cpu().numpy(), W.grad.numpy()) < GRAD_TOL, ctx + " d weight"
                 assert H.rel_err(c.bias.grad.cpu().numpy(), b.grad.numpy()) < GRAD_TOL, ctx + " d bias"
 
 
-def test_bcl_chain_backward_vs_oracle_chain(dev):
+def test_bcl_chain_backward_vs_oracle_chain(dev, monkeypatch):
     """The five E-Net BCLs chained as reference nets/enet.py:113-141 (level l's input = cat(el_minus_gr_l, level l-1's
     output)), loss on bcn5's output: gradients of the stem features and of all 20 weight / bias tensors against the
-    float64 oracle chain's autograd."""
+    float64 oracle chain's autograd (same ReLU active sets, checked against the chained forward tolerance)."""
+    from efgh_b200 import bilateralNN
     from oracle import bcl as obcl
     data = _lattice("os1-64-16k", dev)
     mods = [_module(li, dev, 40 + li) for li in range(5)]
     g = torch.Generator().manual_seed(7)
     feat0 = torch.randn(1, 32, data[0]["pc1_barycentric"].shape[-1], generator=g)
     gout = torch.randn(1, 256, data[4]["pc1_hash_cnt"], generator=g)
+    keep = {}
+    monkeypatch.setattr(bilateralNN, "DEBUG_KEEP", keep)
     x = feat0.to(dev).requires_grad_(True)
     h = x
+    masks = []
     for d, m in zip(data, mods):
         h = m(torch.cat((d["pc1_el_minus_gr"], h), 1), d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
+        masks.append((keep["ys"][0] > 0).cpu())
     h.backward(gout.to(dev))
     f = feat0.double().requires_grad_(True)
     ref_w = []
     r = f
-    for d, m in zip(data, mods):
-        convs = [(c.weight.detach().cpu().double().requires_grad_(True), c.bias.detach().cpu().double().requires_grad_(True))
-                 for c in m.blur_conv if isinstance(c, torch.nn.Conv2d)]
+    flips = []
+    for li, (d, m) in enumerate(zip(data, mods)):
+        convs = _oracle_convs(m)
         ref_w.append(convs)
+        pre = []
         r = obcl.bcl_forward(torch.cat((d["pc1_el_minus_gr"].cpu().double(), r), 1), d["pc1_barycentric"].cpu(),
-                             d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs, dtype=torch.float64)
+                             d["pc1_lattice_offset"].cpu(), d["pc1_blur_neighbors"].cpu(), convs, dtype=torch.float64,
+                             relu_masks=[masks[li]], pre_acts=pre)
+        flips.append(_check_active_set(masks[li], pre[0], 5e-5, "chain level %d" % li))
+    print("ReLU elements at the kink per level:", flips)
     r.backward(gout.double())
     assert H.rel_err(h.detach().cpu().numpy(), r.detach().numpy()) < 5e-5
     assert H.rel_err(x.grad.cpu().numpy(), f.grad.numpy()) < CHAIN_GRAD_TOL, "d stem features"
@@ -139,7 +181,7 @@ def test_weight_cache_sees_data_edits_and_device_moves(dev):
     args = (d["pc1_barycentric"], d["pc1_lattice_offset"], d["pc1_blur_neighbors"], None, None)
     with torch.no_grad():
         y0 = m(feat, *args).clone()
-        assert torch.equal(m(feat, *args), y0)                      # cached path, same result
+        assert H.rel_err(m(feat, *args).cpu().numpy(), y0.cpu().numpy()) < 1e-6     # cached path (the atomic splat sums in arrival order)
         m.blur_conv[0].weight.mul_(2.0)                              # in-place through the tensor: version bump
         y1 = m(feat, *args).clone()
         assert not torch.allclose(y1, y0)

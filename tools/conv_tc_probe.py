@@ -46,5 +46,5 @@ for ns in (3, 1):
     _capi.check(L.efgh_bcl_conv_tc(Y.data_ptr(), M1, M1, b0.data_ptr(), 1, None, 32, 0, 1, H, None, img1.data_ptr(),
                                    b1.data_ptr(), M2, 0, Z.data_ptr(), M2, ns, 0, st), "conv2")
     torch.cuda.synchronize()
-    print("chain nsplit=%d groups=%d rel err %.3e" % (ns, L.efgh_bcl_conv_tc_groups(F * C), float((Z - ref).abs().max() / ref.abs().max())), flush=True)
+    print("chain nsplit=%d groups=%d rel err %.3e" % (ns, L.efgh_bcl_conv_tc_groups(F * C, M), float((Z - ref).abs().max() / ref.abs().max())), flush=True)
 print("probe done")

@@ -22,7 +22,7 @@ for (H, C, F, M) in [(100654, 36, 15, 32), (62551, 36, 15, 64), (23050, 68, 15, 
             L.efgh_debug_set_conv_flags(gc)
             img = torch.empty(L.efgh_bcl_packed_weight_bytes(F * C, M, ns) // 4, device=dev)
             _capi.check(L.efgh_bcl_pack_weights(Wt.data_ptr(), F * C, M, ns, img.data_ptr(), st), "pack")
-            acc = 1 if L.efgh_bcl_conv_tc_groups(F * C) > 1 else 0
+            acc = 1 if L.efgh_bcl_conv_tc_groups(F * C, M) > 1 else 0
             def run():
                 _capi.check(L.efgh_bcl_conv_tc(X.data_ptr(), C, C, None, 0, nbr.data_ptr() if nbr is not None else None, 32, H, F, H, None,
                                                img.data_ptr(), None, M, 0, Y.data_ptr(), M, ns, acc, st), "conv")
@@ -36,5 +36,5 @@ for (H, C, F, M) in [(100654, 36, 15, 32), (62551, 36, 15, 64), (23050, 68, 15, 
             b.record()
             torch.cuda.synchronize()
             print("H=%d C=%d F=%d M=%d nsplit=%d group_chunks=%s groups=%d: %.1f us" %
-                  (H, C, F, M, ns, "flags=0x%x" % gc, L.efgh_bcl_conv_tc_groups(F * C), a.elapsed_time(b) / 20 * 1e3), flush=True)
+                  (H, C, F, M, ns, "flags=0x%x" % gc, L.efgh_bcl_conv_tc_groups(F * C, M), a.elapsed_time(b) / 20 * 1e3), flush=True)
 L.efgh_debug_set_conv_flags(0)

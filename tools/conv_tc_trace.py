@@ -17,7 +17,7 @@ def run(H, C, F, M, label, flags=0, show=0):
     _capi.check(L.efgh_bcl_pack_weights(Wt.data_ptr(), F * C, M, 3, img.data_ptr(), st), "pack")
     Y = torch.zeros(H, M, device=dev)
     trace = torch.zeros(5 * CAP * 2, dtype=torch.int64, device=dev)
-    groups = L.efgh_bcl_conv_tc_groups(F * C)
+    groups = L.efgh_bcl_conv_tc_groups(F * C, M)
     for rep in range(3):
         trace.zero_()
         L.efgh_debug_set_conv_trace.argtypes = [ctypes.c_void_p]

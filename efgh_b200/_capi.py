@@ -44,6 +44,8 @@ SIGNATURES = {
     "efgh_bcl_normalize": (i32, [vp, i64, i32, vp, vp, i64, vp, i32, vp]),
     "efgh_bcl_bias_act": (i32, [vp, i64, i32, i64, vp, vp, i32, vp]),
     "efgh_bcl_conv_dgrad": (i32, [vp, i64, vp, i64, i32, i32, vp, i32, i64, i32, i64, vp, vp, i32, vp, i64, vp]),
+    "efgh_bcl_act_bwd": (i32, [vp, i64, vp, i64, i32, i32, i64, vp, vp]),
+    "efgh_bcl_loss_half_mean_square": (i32, [vp, i64, i32, vp, i32, vp, i64, vp, i64, vp]),
     "efgh_bcl_conv_wgrad": (i32, [vp, i64, i32, vp, vp, i32, i64, i32, i64, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
 }
 

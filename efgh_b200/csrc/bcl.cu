@@ -781,6 +781,59 @@ k_wgrad(const float *__restrict__ X, int64_t ldX, int C, const float *__restrict
   }
 }
 
+// dX[h, :] *= act'(Y[h, :]) in place, rows from the device-side count (backward of the ReLU between the two
+// convolutions; the activation's derivative is read off its output)
+__global__ void k_act_bwd(float *__restrict__ dX, int64_t ldX, const float *__restrict__ Yact, int64_t ldY, int C, int act,
+                          int rows_host, const int32_t *rows_dev) {
+  const int rows = rows_dev ? min(*rows_dev, rows_host) : rows_host;
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)rows * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t h = i / C4;
+    const int c4 = (int)(i - h * C4);
+    float4 *d = reinterpret_cast<float4 *>(dX + h * ldX) + c4;
+    const float4 y = __ldg(reinterpret_cast<const float4 *>(Yact + h * ldY) + c4);
+    float4 v = *d;
+    v.x *= act_bwd(y.x, act); v.y *= act_bwd(y.y, act); v.z *= act_bwd(y.z, act); v.w *= act_bwd(y.w, act);
+    *d = v;
+  }
+}
+
+// Training loss on the last level's output of a batch of scans (rows [start[b], start[b+1]) belong to scan b):
+//   loss = (1/B) sum_b 0.5 * mean(Z_b^2),   dZ[h, :] = Z[h, :] / (B * rows_b * C)
+// One pass: the gradient is written and the loss accumulated (block reduction + one atomic per CTA).
+__global__ void __launch_bounds__(256)
+k_loss_hms(const float *__restrict__ Z, int64_t ldZ, int C, const int32_t *__restrict__ start, int B, float *__restrict__ dZ,
+           int64_t ldD, float *__restrict__ loss, int rows_host) {
+  __shared__ int s_start[65];
+  __shared__ float s_red[8];
+  for (int b = threadIdx.x; b <= B; b += blockDim.x) s_start[b] = start[b];
+  __syncthreads();
+  const int rows = min(s_start[B], rows_host);
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)rows * C4;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i / C4);
+    const int c4 = (int)(i - (int64_t)h * C4);
+    int lo = 0, hi = B;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_start[mid] <= h) lo = mid; else hi = mid; }
+    const float scale = 1.0f / ((float)B * (float)(s_start[lo + 1] - s_start[lo]) * (float)C);
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(Z + (int64_t)h * ldZ) + c4);
+    reinterpret_cast<float4 *>(dZ + (int64_t)h * ldD)[c4] = make_float4(z.x * scale, z.y * scale, z.z * scale, z.w * scale);
+    acc += 0.5f * scale * (z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    if (t != 0.f) atomicAdd(loss, t);
+  }
+}
+
 template <typename F>
 int dispatch_idx(int idx_bits, F &&f) {
   if (idx_bits == 64) return f((int64_t)0);
@@ -1001,4 +1054,29 @@ extern "C" int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const flo
     EFGH_LAUNCH_CHECK();
     return EFGH_OK;
   });
+}
+
+extern "C" int efgh_bcl_act_bwd(float *dX, int64_t ldX, const float *act_out, int64_t ldA, int C, int act, int64_t rows,
+                                const int32_t *rows_dev, void *stream) {
+  EFGH_REQUIRE(C > 0 && C % 4 == 0 && ldX % 4 == 0 && ldA % 4 == 0 && rows >= 0 && rows < (1ll << 31), "efgh_bcl_act_bwd: bad sizes");
+  if (rows == 0 || act == 0) return EFGH_OK;
+  EFGH_REQUIRE(dX && act_out && (reinterpret_cast<uintptr_t>(dX) & 15) == 0 && (reinterpret_cast<uintptr_t>(act_out) & 15) == 0,
+               "efgh_bcl_act_bwd: null or unaligned pointer");
+  k_act_bwd<<<grid_for(rows * (C / 4), 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(dX, ldX, act_out, ldA, C, act, (int)rows,
+                                                                                          rows_dev);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
+}
+
+extern "C" int efgh_bcl_loss_half_mean_square(const float *Z, int64_t ldZ, int C, const int32_t *scan_start, int B, float *dZ,
+                                              int64_t ldD, float *loss, int64_t rows_cap, void *stream) {
+  EFGH_REQUIRE(C > 0 && C % 4 == 0 && ldZ % 4 == 0 && ldD % 4 == 0 && B >= 1 && B <= 64 && rows_cap >= 0 && rows_cap < (1ll << 31),
+               "efgh_bcl_loss_half_mean_square: bad sizes");
+  EFGH_REQUIRE(Z && dZ && loss && scan_start, "efgh_bcl_loss_half_mean_square: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EFGH_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  if (rows_cap == 0) return EFGH_OK;
+  k_loss_hms<<<grid_for(rows_cap * (C / 4), 256, 4), 256, 0, s>>>(Z, ldZ, C, scan_start, B, dZ, ldD, loss, (int)rows_cap);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
 }

@@ -45,7 +45,7 @@ def _on_own_device(fn):
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
                  vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
-                 precision="3xtf32", batch=1, gather_splat=True, stem=None):
+                 precision="3xtf32", batch=1, gather_splat=True, stem=None, train=False):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
         vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
@@ -57,11 +57,15 @@ class ScanPipeline(object):
         nets/enet.py:24-28; W as Conv1d weights (out, in, 1)): the level-0 splat then COMPUTES the stem features from
         the cloud (SURVEY.md §8 f1) and enqueue() ignores feat0;
         batch: scans per launch sequence, each of n_points points (inputs are then (3, batch*n_points) /
-        (C, batch*n_points), scan b in columns [b*n_points, (b+1)*n_points))."""
+        (C, batch*n_points), scan b in columns [b*n_points, (b+1)*n_points));
+        train: keep what backward() needs (normalisation factors, activated conv1 outputs) and allocate the gradient
+        buffers; weights can then be replaced between steps with load_weights()."""
         self.dev = torch.device(device)
         self.L = _capi.lib()
         self.B = int(batch)
         assert 1 <= self.B <= 64
+        self.train = bool(train)
+        assert not (train and stem is not None), "training: the stem runs in torch (autograd); pass its output as feat0"
         self.gather_splat = bool(gather_splat)
         self.level0_splat = "vector-atomic scatter + normalise"
         self.stem = None
@@ -131,23 +135,27 @@ class ScanPipeline(object):
                     "Y": torch.empty((h_cap, cmid), dtype=f32, device=dev),
                     "Z": torch.empty((h_cap, cout), dtype=f32, device=dev),
                 }
-                (W0, b0), (W1, b1) = weights[li]
-                M0, C0, F0, _ = W0.shape
-                assert (M0, C0, F0) == (cmid, cin, F)
-                lv["Wt0"] = W0.detach().to(dev, f32)[:, :, :, 0].permute(2, 1, 0).reshape(F * cin, cmid).contiguous()
-                lv["b0"] = b0.detach().to(dev, f32).contiguous()
-                lv["Wt1"] = W1.detach().to(dev, f32)[:, :, 0, 0].t().contiguous()
-                lv["b1"] = b1.detach().to(dev, f32).contiguous()
                 lv["tc"] = bool(self.nsplit and self.L.efgh_bcl_conv_tc_supported(cin, F, cmid, self.nsplit)
                                 and self.L.efgh_bcl_conv_tc_supported(cmid, 1, cout, self.nsplit)
                                 and self.L.efgh_bcl_conv_tc_groups(cmid, cout) == 1)
                 if lv["tc"]:
                     for nm, K, M in (("img0", F * cin, cmid), ("img1", cmid, cout)):
-                        img = torch.empty(self.L.efgh_bcl_packed_weight_bytes(K, M, self.nsplit) // 4, dtype=f32, device=dev)
-                        _capi.check(self.L.efgh_bcl_pack_weights(lv["Wt" + nm[-1]].data_ptr(), K, M, self.nsplit, img.data_ptr(),
-                                                                 torch.cuda.current_stream(dev).cuda_stream), "efgh_bcl_pack_weights")
-                        lv[nm] = img
+                        lv[nm] = torch.empty(self.L.efgh_bcl_packed_weight_bytes(K, M, self.nsplit) // 4, dtype=f32, device=dev)
                     lv["split0"] = self.L.efgh_bcl_conv_tc_groups(F * cin, cmid) > 1
+                if self.train:
+                    assert lv["tc"] and self.gather_splat, "training needs the tensor-core convolution and the gather-form splat"
+                    cg = cin - 4                                       # channels that carry a gradient (all but el_minus_gr)
+                    assert self.L.efgh_bcl_conv_tc_supported(cmid, F, cg, self.nsplit) and self.L.efgh_bcl_conv_tc_supported(cout, 1, cmid, self.nsplit)
+                    lv["cg"] = cg
+                    lv["inv"] = torch.zeros((h_cap + 1,), dtype=f32, device=dev)
+                    lv["dA"] = torch.zeros((h_cap + 1, cmid), dtype=f32, device=dev)       # row 0: the sink row of the gather-form dgrad
+                    lv["dS"] = torch.zeros((h_cap + 1, cg), dtype=f32, device=dev)
+                    lv["dZ"] = torch.zeros((h_cap, cout), dtype=f32, device=dev)
+                    lv["imgD0"] = torch.empty(self.L.efgh_bcl_packed_weight_bytes(F * cmid, cg, self.nsplit) // 4, dtype=f32, device=dev)
+                    lv["imgD1"] = torch.empty(self.L.efgh_bcl_packed_weight_bytes(cout, cmid, self.nsplit) // 4, dtype=f32, device=dev)
+                    lv["splitD0"] = self.L.efgh_bcl_conv_tc_groups(F * cmid, cg) > 1
+                    offs = [tuple(o) for o in self.gd.radius2offset[radius].tolist()]
+                    lv["mirror"] = [offs.index(tuple(-v for v in o)) for o in offs]     # tap f <-> the tap with the negated offset
                 if self.batch_api:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, lv["table"], n_cap))
                 else:
@@ -157,12 +165,56 @@ class ScanPipeline(object):
                 n_cap_scan = min(4 * n_cap_scan, cap_scan)
                 prev_c = cout
             self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            if self.train:        # weight gradients: one flat buffer (one memset per step), views per level
+                sizes = []
+                for lv in self.levels:
+                    sizes += [lv["F"] * lv["cin"] * lv["cmid"], lv["cmid"], lv["cmid"] * lv["cout"], lv["cout"]]
+                self._gflat = torch.zeros(sum(sizes), dtype=f32, device=dev)
+                o = 0
+                for lv in self.levels:
+                    for nm, shape in (("gWt0", (lv["F"] * lv["cin"], lv["cmid"])), ("gb0", (lv["cmid"],)),
+                                      ("gWt1", (lv["cmid"], lv["cout"])), ("gb1", (lv["cout"],))):
+                        n = int(np.prod(shape))
+                        lv[nm] = self._gflat[o:o + n].view(shape)
+                        o += n
+                self._loss = torch.zeros((), dtype=f32, device=dev)
+                self._dfeat0 = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
+                self._side = None
+            self.load_weights(weights)
             self._starts0 = [b * self.n_scan for b in range(self.B + 1)]
             self.scan_start = torch.tensor(self._starts0, dtype=i32, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
         # per launch sequence: clear/points/assign, vertices, zero, splat (+ normalise | level-0 transpose), conv1, conv2
         self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 2) + sum(0 if lv["gs"] else 1 for lv in self.levels)
+
+    @_on_own_device
+    def load_weights(self, weights):
+        """(Re-)lay the convolution weights for the kernels: (K, M) matrices, packed tensor-core images and - when
+        training - the images of the two data-gradient convolutions.  Stream-ordered on the current stream, no host
+        sync; previously captured graphs stay valid (same buffers)."""
+        L, ck = self.L, _capi.check
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        f32 = torch.float32
+        for lv, ((W0, b0), (W1, b1)) in zip(self.levels, weights):
+            F, cin, cmid, cout = lv["F"], lv["cin"], lv["cmid"], lv["cout"]
+            assert tuple(W0.shape) == (cmid, cin, F, 1) and tuple(W1.shape) == (cout, cmid, 1, 1)
+            W0 = W0.detach().to(self.dev, f32)
+            W1 = W1.detach().to(self.dev, f32)
+            lv["Wt0"] = W0[:, :, :, 0].permute(2, 1, 0).reshape(F * cin, cmid).contiguous()
+            lv["b0"] = b0.detach().to(self.dev, f32).contiguous()
+            lv["Wt1"] = W1[:, :, 0, 0].t().contiguous()
+            lv["b1"] = b1.detach().to(self.dev, f32).contiguous()
+            if lv["tc"]:
+                for nm, K, M in (("0", F * cin, cmid), ("1", cmid, cout)):
+                    ck(L.efgh_bcl_pack_weights(lv["Wt" + nm].data_ptr(), K, M, self.nsplit, lv["img" + nm].data_ptr(), s), "efgh_bcl_pack_weights")
+            if self.train:
+                # conv1's data gradient as a gather over the same neighbour table: dS[g, c] = sum_t sum_m dY[nbr[t,g], m] W0[m, c, mirror(t)]
+                cg = lv["cg"]
+                Wg = W0[:, 4:, :, 0][:, :, lv["mirror"]].permute(2, 0, 1).reshape(F * cmid, cg).contiguous()
+                ck(L.efgh_bcl_pack_weights(Wg.data_ptr(), F * cmid, cg, self.nsplit, lv["imgD0"].data_ptr(), s), "efgh_bcl_pack_weights")
+                Wd = W1[:, :, 0, 0].contiguous()                        # (K = cout, N = cmid)
+                ck(L.efgh_bcl_pack_weights(Wd.data_ptr(), cout, cmid, self.nsplit, lv["imgD1"].data_ptr(), s), "efgh_bcl_pack_weights")
 
     @_on_own_device
     def set_scan_sizes(self, sizes):
@@ -264,7 +316,7 @@ class ScanPipeline(object):
                     # registers through the lattice's vertex -> contributions lists, normalised, written once
                     ck(L.efgh_bcl_splat_gather(lv["prow"].data_ptr(), prev_ptr, prev_sn, prev_c, lv["voff"].data_ptr(),
                                                lv["contrib"].data_ptr(), h_cap, h_dev, 1 if self.use_norm else 0, S, cin,
-                                               None, s), "efgh_bcl_splat_gather")
+                                               lv["inv"].data_ptr() if self.train else None, s), "efgh_bcl_splat_gather")
                     return
                 if li == 0 and self.stem is not None:
                     # [el_minus_gr ; conv_in(xyz)]: the stem's three pointwise layers run on the splat's shared-memory tile
@@ -279,8 +331,8 @@ class ScanPipeline(object):
                                       lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32, n_cap, 1, S, cin,
                                       lv["wsum"].data_ptr() if self.use_norm else None, s), "efgh_bcl_scatter")
                 if self.use_norm:
-                    ck(L.efgh_bcl_normalize(S, cin, cin, lv["wsum"].data_ptr(), None, h_cap + 1, h_dev, 1, s),
-                       "efgh_bcl_normalize")
+                    ck(L.efgh_bcl_normalize(S, cin, cin, lv["wsum"].data_ptr(), lv["inv"].data_ptr() if self.train else None,
+                                            h_cap + 1, h_dev, 1, s), "efgh_bcl_normalize")
             timed("L%d.splat" % li, splat)
             if lv["tc"]:
                 # conv1 on tensor cores: long contraction -> partial sums added in L2, bias + ReLU deferred to
@@ -291,9 +343,12 @@ class ScanPipeline(object):
                     ck(L.efgh_bcl_conv_tc(S, cin, cin, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, lv["F"], h_cap, h_dev,
                                           lv["img0"].data_ptr(), lv["b0"].data_ptr(), lv["cmid"], _ACT["relu"], lv["Y"].data_ptr(),
                                           lv["cmid"], self.nsplit, 1 if split else 0, s), "efgh_bcl_conv_tc")
+                    if split and self.train:    # backward needs the ACTIVATED conv1 output: apply the deferred bias + ReLU in place
+                        ck(L.efgh_bcl_bias_act(lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], h_cap, h_dev, lv["b0"].data_ptr(), _ACT["relu"], s),
+                           "efgh_bcl_bias_act")
                 timed("L%d.conv1" % li, conv1)
                 timed("L%d.conv2" % li, lambda: ck(L.efgh_bcl_conv_tc(
-                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], lv["b0"].data_ptr() if split else None, _ACT["relu"], None, 32, 0,
+                    lv["Y"].data_ptr(), lv["cmid"], lv["cmid"], lv["b0"].data_ptr() if split and not self.train else None, _ACT["relu"], None, 32, 0,
                     1, h_cap, h_dev, lv["img1"].data_ptr(), lv["b1"].data_ptr(), lv["cout"], self.final_act, lv["Z"].data_ptr(),
                     lv["cout"], self.nsplit, 0, s), "efgh_bcl_conv_tc"))
             else:
@@ -309,6 +364,108 @@ class ScanPipeline(object):
             prev_ptr, prev_sc, prev_sn, prev_c = lv["Z"].data_ptr(), 1, lv["cout"], lv["cout"]
             n_dev = h_dev
         return self.levels[-1]["Z"]
+
+    # ------------------------------------------------------------------------------------------
+    # training (SURVEY.md §8 row a17 for a whole batch; reference: autograd over nets/bilateralNN.py:148-263)
+    @_on_own_device
+    def loss_half_mean_square(self, stream=None):
+        """loss = mean over the B scans of 0.5 * mean(Z_b^2) of the last level's output; fills the last level's dZ.
+        Returns (loss 0-d device tensor, dZ buffer).  Stream-ordered, no host sync."""
+        assert self.train
+        lv = self.levels[-1]
+        s = (stream if stream is not None else torch.cuda.current_stream(self.dev)).cuda_stream
+        seg = lv["info"].data_ptr() if self.batch_api else None
+        _capi.check(self.L.efgh_bcl_loss_half_mean_square(lv["Z"].data_ptr(), lv["cout"], lv["cout"], seg, self.B, lv["dZ"].data_ptr(),
+                                                          lv["cout"], self._loss.data_ptr(), lv["h_cap"], s), "efgh_bcl_loss_half_mean_square")
+        return self._loss, lv["dZ"]
+
+    @_on_own_device
+    def backward(self, dZ=None, stream=None):
+        """Backward of the last enqueue() through all levels: the last level's dZ buffer (filled by the caller or by
+        loss_half_mean_square; vertex-major (h_cap, C_out)) -> weight gradients (weight_grads()) and the gradient of
+        feat0, returned as a (C_stem, N) tensor (a buffer of the pipeline).
+
+        Per level, last to first (all counts stay on the device):
+          conv2: dA = dZ W1 on the tensor cores, written below the sink row of dA; dW1, db1 (efgh_bcl_conv_wgrad)
+          ReLU:  dA *= (Y > 0) in place
+          conv1: dW0, db0 from the gathered splat matrix; dS = gather-form convolution of dA with mirrored taps over the
+                 channels that carry a gradient (all but the 4 el_minus_gr channels) - valid because the neighbour
+                 table is mirror-symmetric unless EFGH_ST_ALIASED is set (checked by counts())
+          splat: d(previous output)[n, :] = sum_r bary[r, n] * inv[row] * dS[row, :] (efgh_bcl_gather) -> the previous level's dZ
+        The weight-gradient kernels only feed the optimizer, so they run on a side stream next to the data-gradient chain."""
+        assert self.train
+        L, ck = self.L, _capi.check
+        main = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        s = main.cuda_stream
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        side = self._side
+        ss = side.cuda_stream
+        with torch.cuda.stream(main):
+            if dZ is not None and dZ.data_ptr() != self.levels[-1]["dZ"].data_ptr():
+                self.levels[-1]["dZ"][:dZ.shape[0]].copy_(dZ)
+            self._gflat.zero_()
+        inv_of = (lambda lv: lv["inv"].data_ptr()) if self.use_norm else (lambda lv: None)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        n_dev_top = (self.scan_start.data_ptr() + 4 * self.B) if self.batch_api else None
+        for li in range(self.nlev - 1, -1, -1):
+            lv = self.levels[li]
+            st = self.states[li].data_ptr()
+            h_dev, h_cap = st + 4, lv["h_cap"]
+            cin, cmid, cout, cg, F = lv["cin"], lv["cmid"], lv["cout"], lv["cg"], lv["F"]
+            dZl, dA, dS = lv["dZ"].data_ptr(), lv["dA"].data_ptr(), lv["dS"].data_ptr()
+            dA1 = dA + 4 * cmid                                  # row 1: vertex 0
+            # --- conv2
+            if self.final_act:
+                ck(L.efgh_bcl_act_bwd(dZl, cout, lv["Z"].data_ptr(), cout, cout, self.final_act, h_cap, h_dev, s), "efgh_bcl_act_bwd")
+            ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)          # dZ of this level is complete
+            ck(L.efgh_bcl_conv_wgrad(lv["Y"].data_ptr(), cmid, cmid, None, None, 32, 0, 1, h_cap, h_dev, dZl, cout, None, 0, 0, cout,
+                                     lv["gWt1"].data_ptr(), lv["gb1"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
+            ck(L.efgh_bcl_conv_tc(dZl, cout, cout, None, 0, None, 32, 0, 1, h_cap, h_dev, lv["imgD1"].data_ptr(), None, cmid, 0,
+                                  dA1, cmid, self.nsplit, 0, s), "efgh_bcl_conv_tc(dgrad 1x1)")
+            ck(L.efgh_bcl_act_bwd(dA1, cmid, lv["Y"].data_ptr(), cmid, cmid, _ACT["relu"], h_cap, h_dev, s), "efgh_bcl_act_bwd")
+            # --- conv1
+            ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)          # masked dA is complete
+            ck(L.efgh_bcl_conv_wgrad(lv["S"].data_ptr(), cin, cin, None, lv["nbr32"].data_ptr(), 32, h_cap, F, h_cap, h_dev, dA1, cmid,
+                                     None, 0, 0, cmid, lv["gWt0"].data_ptr(), lv["gb0"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
+            split = lv["splitD0"]
+            if split:
+                ck(L.efgh_bcl_zero(None, cg, cg, None, dS + 4 * cg, cg, cg, h_cap, h_dev, 0, s), "efgh_bcl_zero")
+            ck(L.efgh_bcl_conv_tc(dA, cmid, cmid, None, 0, lv["nbr32"].data_ptr(), 32, h_cap, F, h_cap, h_dev, lv["imgD0"].data_ptr(),
+                                  None, cg, 0, dS + 4 * cg, cg, self.nsplit, 1 if split else 0, s), "efgh_bcl_conv_tc(dgrad)")
+            # --- splat adjoint -> gradient of the previous level's output (or of feat0)
+            n_cap = lv["n_cap"]
+            if li > 0:
+                prev = self.levels[li - 1]
+                n_dev = self.states[li - 1].data_ptr() + 4
+                ck(L.efgh_bcl_gather(dS, cg, cg, inv_of(lv), n_cap, n_dev, lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32,
+                                     n_cap, 1, None, prev["dZ"].data_ptr(), 1, cg, s), "efgh_bcl_gather")
+            else:
+                ck(L.efgh_bcl_gather(dS, cg, cg, inv_of(lv), n_cap, n_dev_top, lv["bary"].data_ptr(), n_cap, lv["loff32"].data_ptr(), 32,
+                                     n_cap, 1, None, self._dfeat0.data_ptr(), self._dfeat0.stride(0), 1, s), "efgh_bcl_gather")
+        ev = torch.cuda.Event()
+        ev.record(side)
+        main.wait_event(ev)
+        return self._dfeat0
+
+    def aliased_levels(self):
+        """Levels whose neighbour table lost its mirror symmetry (EFGH_ST_ALIASED: a neighbour key left the key box and the
+        reference's key2int aliasing found another vertex) - backward()'s gather-form data gradient is not valid there.
+        Synchronising read."""
+        host = self.states.cpu()
+        return [li for li in range(self.nlev) if int(host[li, 2]) & 8]
+
+    def weight_grads(self):
+        """[[(dW0 (C_mid, C_in, F, 1), db0), (dW1 (C_out, C_mid, 1, 1), db1)] per level] in the reference's parameter layout
+        (views of the pipeline's flat gradient buffer: consume them before the next backward())."""
+        out = []
+        for lv in self.levels:
+            g0 = lv["gWt0"].view(lv["F"], lv["cin"], lv["cmid"]).permute(2, 1, 0).unsqueeze(-1)
+            g1 = lv["gWt1"].t()[:, :, None, None]
+            out.append([(g0, lv["gb0"]), (g1, lv["gb1"])])
+        return out
 
     @_on_own_device
     def graph_for(self, pc, feat0, stream):

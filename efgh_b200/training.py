@@ -68,7 +68,7 @@ class BatchedTrainer(object):
     per-scan host work.  (The E-Net head is a per-scan Conv1d / BatchNorm stack outside the lattice path;
     ModulePathTrainer includes it.)"""
 
-    def __init__(self, clouds, dev, world=1, lr=1e-4, seed=0, vertex_cap_factor=1.0, precision="3xtf32"):
+    def __init__(self, clouds, dev, world=1, lr=1e-4, seed=0, vertex_cap_factor=2.0, precision="3xtf32"):
         from .pipeline import ScanPipeline
         torch.manual_seed(seed)
         self.dev, self.world = dev, world
@@ -86,6 +86,7 @@ class BatchedTrainer(object):
             self.pipe = ScanPipeline(n, synth.SCALE_MAP, plan, self._weights(), dev, vertex_cap_factor=vertex_cap_factor,
                                      emit_int64=False, batch=B, precision=precision, train=True)
         self.allreduce_calls = 0
+        self._checked = False
 
     def _weights(self):
         return [[(c.weight.detach(), c.bias.detach()) for c in m.blur_conv if isinstance(c, nn.Conv2d)] for m in self.bcns]
@@ -101,6 +102,13 @@ class BatchedTrainer(object):
             feat0 = self.stem(self.pc[None])[0]                # (32, B*n), autograd
             Z = pipe.enqueue(self.pc, feat0.detach())
             loss, dZ = pipe.loss_half_mean_square()            # per-scan means, device-side row counts
+            if not self._checked:      # first step only (synchronising): capacities and the symmetry backward() relies on
+                pipe.counts()
+                bad = pipe.aliased_levels()
+                if bad:
+                    raise RuntimeError("BatchedTrainer: neighbour tables of levels %s are not mirror-symmetric (aliased keys); "
+                                       "use ModulePathTrainer for such clouds" % bad)
+                self._checked = True
             dfeat0 = pipe.backward(dZ)
             feat0.backward(dfeat0)
             for m, g in zip(self.bcns, pipe.weight_grads()):

@@ -281,6 +281,21 @@ int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const float *row_sca
                         int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *dY, int64_t ldY,
                         const float *act_out, int64_t ldA, int act, int M, float *dWt, float *dbias, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training helpers of the batched pipeline (reference iterater.py:35-43: forward -> loss -> backward).
+ *
+ * efgh_bcl_act_bwd: dX[h, :] *= act'(act_out[h, :]) in place over rows [0, rows) (rows_dev: device-side count) -
+ *   the backward of the ReLU that reference nets/bilateralNN.py:111-115 puts between the two convolutions
+ *   (autograd's threshold_backward); act as in efgh_bcl_conv (1 ReLU, 2 LeakyReLU 0.1).
+ * efgh_bcl_loss_half_mean_square: loss = (1/B) sum_b 0.5 * mean(Z_b^2) over the B scans of a batch, Z_b = rows
+ *   [scan_start[b], scan_start[b+1]) of the vertex-major (rows, C) matrix; writes the loss (one float) and its
+ *   gradient dZ in one pass.  A stand-in objective for benchmarks and tests: the reference's losses
+ *   (losses/efghloss.py) act on the E-Net head, which is outside the lattice path. */
+int efgh_bcl_act_bwd(float *dX, int64_t ldX, const float *act_out, int64_t ldA, int C, int act, int64_t rows,
+                     const int32_t *rows_dev, void *stream);
+int efgh_bcl_loss_half_mean_square(const float *Z, int64_t ldZ, int C, const int32_t *scan_start, int B, float *dZ,
+                                   int64_t ldD, float *loss, int64_t rows_cap, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,10 @@ SIGNATURES = {
     "efgh_bcl_normalize": (i32, [vp, i64, i32, vp, vp, i64, vp, i32, vp]),
     "efgh_bcl_bias_act": (i32, [vp, i64, i32, i64, vp, vp, i32, vp]),
     "efgh_bcl_conv_dgrad": (i32, [vp, i64, vp, i64, i32, i32, vp, i32, i64, i32, i64, vp, vp, i32, vp, i64, vp]),
+    "efgh_project_range_image": (i32, [vp, i64, i64, i64, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp]),
+    "efgh_project_depth_image": (i32, [vp, i64, i64, i64, i32, vp, i32, i32, vp, vp, vp]),
+    "efgh_preproc_workspace_bytes": (sz, [i64]),
+    "efgh_preproc_cloud": (i32, [vp, i64, i32, f32, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
     "efgh_bcl_act_bwd": (i32, [vp, i64, vp, i64, i32, i32, i64, vp, vp]),
     "efgh_bcl_loss_half_mean_square": (i32, [vp, i64, i32, vp, i32, vp, i64, vp, i64, vp]),
     "efgh_bcl_conv_wgrad": (i32, [vp, i64, i32, vp, vp, i32, i64, i32, i64, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),

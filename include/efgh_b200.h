@@ -296,6 +296,39 @@ int efgh_bcl_act_bwd(float *dX, int64_t ldX, const float *act_out, int64_t ldA, 
 int efgh_bcl_loss_half_mean_square(const float *Z, int64_t ldZ, int C, const int32_t *scan_start, int B, float *dZ,
                                    int64_t ldD, float *loss, int64_t rows_cap, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Point -> image scatter projections and cloud pre-processing (row f4).
+ *
+ * efgh_project_range_image   replaces reference common/torch_utils.py:11-59 (range_img_from_cartesian_pc_torch):
+ *   pc: (batch, 3, n) float32 (row stride pc_ld, batch stride in elements); img: (batch, 4, height, width) = x, y, z,
+ *   range at pixel (u, v) = (long)((fov_up - asin(z/r)) / (fov_up - fov_down) * (height-1)),
+ *   (long)((-atan2(y, x) + pi) / (2 pi) * (width-1)) for points with fov_down < pitch < fov_up, 0 elsewhere.
+ *   fov_up / fov_down in radians (the reference's lidar_fov_rad[i] * pi, as Python floats).
+ * efgh_project_depth_image   replaces reference common/torch_utils.py:61-103 (depth_img_from_cartesian_pc_torch):
+ *   [x' y' w] = cam_T_velo (batch, 3, 4) @ [pc; 1]; pixel ((long)(y'/w), (long)(x'/w)) inside the image and w > 0
+ *   receives (x, y, z, w).
+ * Duplicate pixels: the point with the LARGEST index wins (the sequential semantics of the reference's
+ * `img[u.tolist(), v.tolist()] = values`); `winner` is a (batch, height, width) int32 scratch that ends up holding
+ * that point index (-1 = empty pixel).
+ *
+ * efgh_preproc_cloud         replaces reference data_loader/loader_utils.py:163-202 (preproc_pcd, without its
+ *   reduce_lidar_line branch): xyzi = the (n, 4) float32 records of a `.bin` scan (loader_utils.py:59-61) in device
+ *   memory; crop to -radius <= x, y < radius keeping the order (use_radius = 0: radius None); if more than num_points
+ *   survive, take points sample[0..num_points) of the CROPPED cloud (the caller draws `sample` - numpy's RNG stays on
+ *   the host: np.random.choice(m, num_points, replace=False)), else zero-pad; then the 4x4 float64 rigid transform.
+ *   out64: (4, num_points) float64 = the reference's return value; out32: (3, num_points) float32 = what the network
+ *   consumes after `.float()` (either may be NULL).  kept_count (device int32) receives the cropped size m - the
+ *   caller needs it to size `sample` (two-phase use: call once with num_points >= n to learn m, or over-provision
+ *   sample).  A sample index outside [0, m) sets bit 0 of the int32 that follows the workspace's index arrays. */
+int efgh_project_range_image(const float *pc, int64_t pc_ld, int64_t batch_stride, int64_t n, int batch, int height,
+                             int width, double fov_up, double fov_down, int32_t *winner, float *img, void *stream);
+int efgh_project_depth_image(const float *pc, int64_t pc_ld, int64_t batch_stride, int64_t n, int batch,
+                             const float *cam_T_velo, int height, int width, int32_t *winner, float *img, void *stream);
+size_t efgh_preproc_workspace_bytes(int64_t n);
+int efgh_preproc_cloud(const float *xyzi, int64_t n, int use_radius, float radius, const int64_t *sample,
+                       int64_t n_sample, int64_t num_points, const double *transform, double *out64, float *out32,
+                       int32_t *kept_count, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

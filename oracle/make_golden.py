@@ -148,9 +148,79 @@ def stem_golden():
         print("stem", name, tuple(out.shape), float(out.abs().mean()))
 
 
+def projection_cases():
+    """Clouds / calibrations of the f3 / f4 fixtures (shared with the tests through the npz files)."""
+    rng = np.random.default_rng(77)
+    full = synth.synth_scan(13, "os1-64-16k")
+    pc = np.stack([full[:, :6000], synth.synth_scan(14, "os1-64-16k")[:, :6000]], 0)          # (2, 3, 6000)
+    pc[1, :, :40] = pc[1, :, 40:80]                     # exact duplicates: same pixel, the later point must win
+    pc[0, :, 100] = 0.0                                 # r = 0 -> NaN pitch -> masked out
+    # a pinhole camera looking along +x (RELLIS-like intrinsics scaled to the test image), small rotation + offset
+    Hc, Wc = 150, 240
+    K = np.array([[170.0, 0, Wc / 2.0], [0, 170.0, Hc / 2.0], [0, 0, 1.0]])
+    R0 = np.array([[0, -1.0, 0], [0, 0, -1.0], [1.0, 0, 0]])                                   # velo (x fwd, y left, z up) -> cam (x right, y down, z fwd)
+    Ts = []
+    for b in range(2):
+        from scipy.spatial.transform import Rotation
+        R = Rotation.from_euler("xyz", rng.uniform(-0.05, 0.05, 3)).as_matrix() @ R0
+        t = rng.uniform(-0.2, 0.2, 3)
+        Ts.append(K @ np.concatenate([R, t[:, None]], 1))
+    return pc.astype(np.float32), np.stack(Ts, 0).astype(np.float32), (Hc, Wc)
+
+
+def projection_golden():
+    """f3: reference common/torch_utils.py:11-103 run LIVE on CPU (single thread: sequential duplicate resolution)
+    -> tests/golden/proj_range.npz, proj_depth.npz; f4: data_loader/loader_utils.py:163-202 -> preproc_*.npz."""
+    c = ref_harness.load_common()
+    tu, lu = c["torch_utils"], c["loader_utils"]
+    os.makedirs(OUT, exist_ok=True)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        pc, T, (Hc, Wc) = projection_cases()
+        size, fov = (32, 512), (0.125, -0.125)          # reference configs/train_rellis.yaml:21 lidar_fov_rad
+        rimg = tu.range_img_from_cartesian_pc_torch(torch.from_numpy(pc.copy()), size, fov, "cpu").numpy()
+        np.savez_compressed(os.path.join(OUT, "proj_range.npz"), pc=pc, size=np.asarray(size), fov=np.asarray(fov), img=rimg)
+        print("range image", rimg.shape, int((rimg[:, 3] > 0).sum()), "pixels set")
+        dimg = tu.depth_img_from_cartesian_pc_torch(torch.from_numpy(pc.copy()), torch.from_numpy(T.copy()), (Hc, Wc), "cpu").numpy()
+        np.savez_compressed(os.path.join(OUT, "proj_depth.npz"), pc=pc, T=T, size=np.asarray((Hc, Wc)), img=dimg)
+        print("depth image", dimg.shape, int((dimg[:, 3] != 0).sum()), "pixels set")
+    finally:
+        torch.set_num_threads(nthreads)
+    # ---- pre-processing: a `.bin`-format scan (n, 4) float32 with points outside the 50 m box; subsample / pad cases
+    rng = np.random.default_rng(5)
+    scan = np.concatenate([synth.synth_scan(15, "os1-64-16k")[:, :5000].T, rng.uniform(0, 1, (5000, 1)).astype(np.float32)], 1)
+    scan[::7, 0] *= 1.6                                  # push every 7th point out of the +-50 m box in x
+    scan[3::11, 1] = -50.0                               # on the closed lower edge (kept)
+    scan[5::13, 1] = 50.0                                # on the open upper edge (dropped)
+    scan = np.ascontiguousarray(scan.astype(np.float32))
+    from scipy.spatial.transform import Rotation
+    Tl = np.eye(4)
+    Tl[:3, :3] = Rotation.from_euler("xyz", [0.31, -0.22, 0.47]).as_matrix()
+    Tl[:3, 3] = [1.3, -0.8, 0.25]
+    for name, num_points in (("subsample", 2048), ("pad", 6000)):
+        import random
+        np.random.seed(1234)
+        state = np.random.get_state()
+        out = lu.preproc_pcd(scan.copy(), {"rand_init_l": Tl}, num_points)
+        # the index set the reference drew: replay the RNG on the cropped size
+        keep = (scan[:, 0] >= -50.) & (scan[:, 0] < 50.) & (scan[:, 1] >= -50.) & (scan[:, 1] < 50.)
+        m = int(keep.sum())
+        sample = np.zeros((0,), np.int64)
+        if num_points < m:
+            np.random.set_state(state)
+            sample = np.random.choice(range(m), size=num_points, replace=False, p=None).astype(np.int64)
+        np.savez_compressed(os.path.join(OUT, "preproc_%s.npz" % name), scan=scan, T=Tl, num_points=np.int64(num_points),
+                            sample=sample, m=np.int64(m), out=np.asarray(out, dtype=np.float64))
+        print("preproc", name, out.shape, "cropped", m)
+
+
 if __name__ == "__main__":
     if "--only-stem" in sys.argv:
         stem_golden()
+    elif "--only-projection" in sys.argv:
+        projection_golden()
     else:
         main()
         stem_golden()
+        projection_golden()

@@ -115,3 +115,46 @@ def load_net_utils():
         spec.loader.exec_module(m)
         _mods["n"] = m
     return _mods["n"]
+
+
+def load_common():
+    """The live reference's common/torch_utils.py (range / depth image projections, :11-103) and
+    data_loader/loader_utils.py (pcd_read :59-61, preproc_pcd :163-202), imported by path.  common/numpy_utils.py
+    needs matplotlib and open3d (absent here; only its drawing helpers use them): stub modules stand in.  The two
+    projection functions build their index tensors with torch.cuda.LongTensor / FloatTensor regardless of `device`
+    (torch_utils.py:50-51); on this GPU-less container those two constructors are pointed at their CPU twins - the
+    arithmetic that runs is the reference's own, on torch's CPU kernels.  Build container only."""
+    if "c" in _mods:
+        return _mods["c"]
+    if not (available() and os.path.isfile(os.path.join(REF_ROOT, "common", "torch_utils.py"))):
+        raise RuntimeError("reference common/ not present at %s" % REF_ROOT)
+    from unittest import mock
+    import torch
+    for name in ("matplotlib", "matplotlib.pyplot", "open3d"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = mock.MagicMock(name=name)
+    pkg = types.ModuleType("common")
+    pkg.__path__ = [os.path.join(REF_ROOT, "common")]
+    saved = sys.modules.get("common")
+    sys.modules["common"] = pkg
+    try:
+        out = {}
+        for key, rel in (("numpy_utils", "common/numpy_utils.py"), ("torch_utils", "common/torch_utils.py"),
+                         ("loader_utils", "data_loader/loader_utils.py")):
+            modname = "common." + key if rel.startswith("common/") else "ref_" + key
+            spec = importlib.util.spec_from_file_location(modname, os.path.join(REF_ROOT, rel))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[modname] = m
+            spec.loader.exec_module(m)
+            out[key] = m
+    finally:
+        if saved is not None:
+            sys.modules["common"] = saved
+    if not torch.cuda.is_available():
+        torch.cuda.LongTensor = lambda t: t.to(torch.int64)
+        torch.cuda.FloatTensor = lambda t: t.to(torch.float32)
+    _mods["c"] = out
+    return out

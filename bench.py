@@ -664,6 +664,10 @@ def run_ours(args):
             extras["module_path"] = module_path_leg(torch, dev, synth, clouds[:4], weights)
         except Exception as e:
             extras["module_path"] = {"error": repr(e)}
+        try:
+            extras["aux_stages"] = aux_leg(torch, dev, synth, clouds[0], measured_peaks())
+        except Exception as e:
+            extras["aux_stages"] = {"error": repr(e)}
         torch.cuda.empty_cache()
         try:
             extras["train"] = train_leg(5, 2)
@@ -748,6 +752,47 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def aux_leg(torch, dev, synth, cloud, peaks):
+    """SURVEY.md §8 rows f3 / f4 beside the lattice path: the point -> image projections (reference
+    common/torch_utils.py:11-103) and the cloud pre-processing (reference data_loader/loader_utils.py:163-202) on one
+    131k-point scan, CUDA-event timed (median of 20, after 3 warm-ups), with their algorithmic bytes (points read once,
+    image written once) against the measured copy bandwidth."""
+    import numpy as np
+    from efgh_b200.projections import range_img_from_cartesian_pc_torch, depth_img_from_cartesian_pc_torch
+    from efgh_b200.preproc import preproc_pcd
+    pc = torch.from_numpy(cloud)[None].to(dev)
+    n = pc.shape[-1]
+    K = np.array([[2813.6, 0, 969.3], [0, 2808.3, 624.0], [0, 0, 1.0]])
+    R0 = np.array([[0, -1.0, 0], [0, 0, -1.0], [1.0, 0, 0]])
+    T = torch.from_numpy((K @ np.concatenate([R0, np.array([[0.03], [-0.1], [-0.12]])], 1)).astype(np.float32))[None].to(dev)
+    scan = torch.cat((pc[0].t() * 1.3, torch.rand(n, 1, device=dev)), 1).contiguous()
+    gts = {"rand_init_l": np.eye(4)}
+    sample = np.random.default_rng(0).permutation(100000)[:65536]
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts)) * 1e3
+
+    out = {}
+    for name, fn, by in (
+            ("range_image_600x3840", lambda: range_img_from_cartesian_pc_torch(pc, (600, 3840), (0.125, -0.125), "cuda"), 12 * n + 16 * 600 * 3840),
+            ("depth_image_1200x1920", lambda: depth_img_from_cartesian_pc_torch(pc, T, (1200, 1920), "cuda"), 12 * n + 16 * 1200 * 1920),
+            ("preproc_131k_to_65536", lambda: preproc_pcd(scan, gts, 65536, sample=sample), 16 * n + 8 * 65536 + 32 * 65536)):
+        us = timed(fn)
+        out[name] = {"us": us, "algorithmic_bytes": by, "hbm_gbs": by / us / 1e3, "hbm_frac": by / us / 1e3 / peaks["hbm_gbs"]}
+    out["note"] = "host-timed wrappers (allocation + 3-4 launches each); latency-bound at one scan per call"
+    return out
 
 
 def module_path_leg(torch, dev, synth, clouds, weights):

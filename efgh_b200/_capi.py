@@ -48,6 +48,8 @@ SIGNATURES = {
     "efgh_project_depth_image": (i32, [vp, i64, i64, i64, i32, vp, i32, i32, vp, vp, vp]),
     "efgh_preproc_workspace_bytes": (sz, [i64]),
     "efgh_preproc_cloud": (i32, [vp, i64, i32, f32, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "efgh_bcl_conv_wgrad_tc_supported": (i32, [i32, i32, i32]),
+    "efgh_bcl_conv_wgrad_tc": (i32, [vp, i64, i32, vp, i32, i64, i32, i64, vp, vp, i64, i32, vp, vp, vp]),
     "efgh_bcl_act_bwd": (i32, [vp, i64, vp, i64, i32, i32, i64, vp, vp]),
     "efgh_bcl_loss_half_mean_square": (i32, [vp, i64, i32, vp, i32, vp, i64, vp, i64, vp]),
     "efgh_bcl_conv_wgrad": (i32, [vp, i64, i32, vp, vp, i32, i64, i32, i64, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),

@@ -41,6 +41,8 @@ _NSPLIT = {"3xtf32": 3, "tf32": 1}
 # Data gradient of the convolutions as a gather-form convolution on the tensor-core kernel (else the scatter-form
 # CUDA-core kernel).
 DGRAD_ON_TENSOR_CORES = os.environ.get("EFGH_DGRAD", "tc") != "scatter"
+# Weight gradient on the tensor cores (tcgen05, 3xTF32, MN-major operands; csrc/wgrad_tc.cu), else the fp32 CUDA-core kernel.
+WGRAD_ON_TENSOR_CORES = os.environ.get("EFGH_WGRAD", "tc") != "ffma"
 
 
 def init_weights(m):
@@ -256,6 +258,15 @@ def conv_wgrad(X, row_scale, nbr, dY, act_out, act, want_bias):
         F, bits, nbp, nb_ld = 1, 64, None, 0
     dWt = torch.zeros((F * C, M), dtype=torch.float32, device=dY.device)
     db = torch.zeros((M,), dtype=torch.float32, device=dY.device) if want_bias else None
+    L = _capi.lib()
+    if (WGRAD_ON_TENSOR_CORES and row_scale is None and L.efgh_bcl_conv_wgrad_tc_supported(C, F, M) and X.stride(0) % 4 == 0
+            and X.data_ptr() % 16 == 0):
+        dYm = _act_bwd(dY, act_out, act)                   # the tensor-core kernel takes the masked gradient
+        if not dYm.is_contiguous() or dYm.data_ptr() % 16:
+            dYm = dYm.contiguous()
+        _capi.check(L.efgh_bcl_conv_wgrad_tc(X.data_ptr(), X.stride(0), C, nbp, bits, nb_ld, F, h, None, dYm.data_ptr(), dYm.stride(0), M,
+                                             dWt.data_ptr(), _capi.ptr(db), _capi.stream_ptr()), "efgh_bcl_conv_wgrad_tc")
+        return dWt, db
     _capi.check(_capi.lib().efgh_bcl_conv_wgrad(X.data_ptr(), X.stride(0), C, _capi.ptr(row_scale), nbp, bits, nb_ld, F,
                                                 h, None, dY.data_ptr(), dY.stride(0), _capi.ptr(act_out),
                                                 act_out.stride(0) if act_out is not None else 0, act, M,

@@ -1,0 +1,433 @@
+// Weight gradient of the lattice convolution on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+//   dWt[k, m] += sum_h A[h, k] * G[h, m],   A[h, f*C + c] = X[nbr[f,h]+1, c]   (gathered splat rows),  G = dY (masked)
+//
+// reference: autograd over nets/bilateralNN.py:240-244 (cuDNN wgrad of the (F,1) convolution over the materialised
+// (1, C, F, H) gathered tensor).  The reduction runs over the lattice VERTICES, i.e. over the row index of both
+// row-major operand arrays, so both tensor-core operands are "MN-major": a gathered row piece (32 consecutive k of one
+// vertex, 128 bytes) is already one row of the canonical MN-major shared-memory tile, and so is a 128-byte piece of a
+// dY row.  tf32 MN-major operands must use the SWIZZLE_128B_BASE32B layout (32-byte chunks XOR-ed with row & 3; layout
+// and descriptor strides established by tools/umma_mn_probe.cu):
+//   tile   = groups of 32 MN elements; inside a group row v (vertex) is 128 bytes; LBO = group stride, SBO = 4 rows
+//   MMA    = M 128 (conv-k) x N (<= 128 output channels) x K 8 (vertices), both operands from shared memory
+//
+//   warps 0-7   producers: per stage of 32 vertices cp.async (LDGSTS, zero-fill) 4 x 32 conv-k of every vertex's
+//               gathered rows and N floats of its dY row into the stage, then split what landed into the TF32-exact
+//               part (which the tensor core obtains by truncating the raw fp32 operand) and the remainder "small",
+//               written to a second tile: 3xTF32 = raw*raw + small*raw + raw*small
+//   warp  8     MMA issuer (one elected lane), fp32 accumulators in TMEM, two accumulator stages
+//   warps 9-12  epilogue: accumulation chains are CUT every 8 stages (256 vertices; the tensor core rounds toward zero
+//               on every accumulate) and summed with round-to-nearest adds into a shared-memory running tile; at the end
+//               of a work item the 128 x N tile is added to dWt in global memory (red.add, one per vertex split)
+// Work item = (128-wide conv-k tile, 128-wide slice of the output channels, vertex range); the vertex count is read
+// from device memory and split so that all SMs have work.
+#include "common.cuh"
+
+namespace efgh {
+namespace {
+
+constexpr int kWM = 128;                       // conv-k rows per tile (MMA M)
+constexpr int kWStageV = 32;                   // vertices per stage (4 MMA K-steps)
+constexpr int kWStages = 2;
+constexpr int kWCutStages = 8;                 // stages per accumulation chain (256 vertices)
+constexpr int kWProducerWarps = 8;
+constexpr int kWMmaWarp = kWProducerWarps, kWEpiWarp0 = kWProducerWarps + 1;
+constexpr int kWThreads = (kWEpiWarp0 + 4) * 32;   // 416
+constexpr int kWTargetItems = 444;             // ~3 work items per SM
+
+__device__ __forceinline__ uint32_t w_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void w_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void w_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) break;
+    __nanosleep(32);
+  }
+}
+__device__ __forceinline__ void w_commit(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+// both operands from shared memory; the whole (converged) warp executes, one elected lane issues
+__device__ __forceinline__ void w_umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// MN-major, SWIZZLE_128B_BASE32B (layout type 1), descriptor version 1: LBO = stride between 32-element MN groups,
+// SBO = stride between 4-row K atoms (512 B with 128-byte rows)
+__device__ __forceinline__ uint64_t w_desc(uint32_t addr, uint32_t group_stride) {
+  const uint32_t lo = ((addr & 0x3ffff) >> 4) | ((group_stride >> 4) << 16);
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128
+__device__ __forceinline__ uint32_t w_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kWM >> 4) << 24);
+}
+__device__ __forceinline__ void w_tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct WgradParams {
+  const float *X; int64_t ldX; int C;
+  const void *nbr; int64_t nbr_ld; int F;
+  int h_host; const int32_t *h_dev;
+  const float *G; int64_t ldG; int M;
+  float *dWt;                                 // (F*C, M) row-major, accumulated into
+  int K, n_kt, n_np, Np;                      // K = F*C; conv-k tiles; output-channel slices of Np columns
+  uint32_t magic_c;
+};
+
+// work item -> (vertex split, conv-k tile, output slice); vertex ranges are whole stages
+struct WItem {
+  int kt, np, st_begin, st_end;
+};
+__device__ __forceinline__ WItem w_item(const WgradParams &p, int item, int n_stages, int vsplit) {
+  const int per = p.n_kt * p.n_np;
+  const int vs = item / per, r = item - vs * per;
+  WItem it;
+  it.np = r / p.n_kt; it.kt = r - it.np * p.n_kt;
+  const int base = n_stages / vsplit, rem = n_stages % vsplit;
+  it.st_begin = vs * base + min(vs, rem);
+  it.st_end = it.st_begin + base + (vs < rem ? 1 : 0);
+  return it;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t w_smem_raw[];
+  const uint32_t smem_base = (w_smem_u32(w_smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = w_smem_raw + (smem_base - w_smem_u32(w_smem_raw));
+  const int Np = p.Np;
+  const uint32_t a_bytes = 4u * 4096u;                         // 4 groups x 32 rows x 128 B
+  const uint32_t g_bytes = (uint32_t)(Np / 32) * 4096u;
+  const uint32_t stage_bytes = 2u * a_bytes + 2u * g_bytes;   // [A raw | A small | G raw | G small]
+  const uint32_t sum_base = smem_base + kWStages * stage_bytes;
+  const int pitch = Np + 4;                                    // floats per row of the running-sum tile
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWStages * stage_bytes + (size_t)kWM * pitch * 4);
+  // barriers: full[2] empty[2] acc_full[2] acc_empty[2]
+  const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 16, bar_acc_full = bar_full + 32, bar_acc_empty = bar_full + 48;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
+  const int n_stages = (H + kWStageV - 1) / kWStageV;
+  const int per = p.n_kt * p.n_np;
+  int vsplit = (kWTargetItems + per - 1) / per;
+  vsplit = max(1, min(vsplit, (n_stages + kWCutStages - 1) / kWCutStages));
+  const int n_items = n_stages > 0 ? per * vsplit : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWStages; ++s) { w_mbar_init(bar_full + 8 * s, kWProducerWarps); w_mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { w_mbar_init(bar_acc_full + 8 * a, 1); w_mbar_init(bar_acc_empty + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(s_tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < kWProducerWarps) {
+    // ===================== producers =====================
+    const int t = threadIdx.x;
+    const int v = (t >> 1) & 31, g = t >> 6, half = t & 1;
+    const bool has_g = g < Np / 32;
+    // destination offsets of this thread's 4 pieces (16 B each) inside a 32-row group: 32-byte chunks XOR (row & 3)
+    uint32_t doff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t u = 4u * half + i;
+      doff[i] = (uint32_t)g * 4096u + (uint32_t)v * 128u + ((((u >> 1) ^ ((uint32_t)v & 3u))) << 5) + (u & 1u) * 16u;
+    }
+    uint32_t count = 0;                                        // stages produced so far (ring position)
+    int rows_next[4];                                          // matrix rows (nbr + 1, 0 = absent) of the stage about to be issued
+    // flattened walk over (item, stage)
+    int item = blockIdx.x;
+    WItem it = item < n_items ? w_item(p, item, n_stages, vsplit) : WItem{0, 0, 0, 0};
+    int st = it.st_begin;
+    int f4[4], c4[4];
+    bool ok4[4];
+    auto setup_item = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = it.kt * kWM + 32 * g + 16 * half + 4 * i;
+        ok4[i] = k < p.K;
+        f4[i] = (int)__umulhi((uint32_t)k, p.magic_c);
+        c4[i] = k - f4[i] * p.C;
+      }
+    };
+    auto fetch_rows = [&](int stage, int *rows) {
+      const int h = stage * kWStageV + v;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = 0;
+        if (h < H && ok4[i]) r = p.nbr ? load_idx<IdxT>(p.nbr, (int64_t)f4[i] * p.nbr_ld + h) + 1 : h + 1;
+        rows[i] = r;
+      }
+    };
+    if (item < n_items) { setup_item(); fetch_rows(st, rows_next); }
+    const int64_t xoff = p.nbr ? 0 : -(int64_t)p.ldX;          // without a neighbour table X has no sink row: row h+1 -> h
+    bool pending = false;                                      // a stage issued but not yet converted
+    uint32_t pend_slot = 0;
+    while (item < n_items || pending) {
+      uint32_t slot = 0;
+      const bool issue = item < n_items;
+      if (issue) {
+        slot = count & 1u;
+        w_mbar_wait(bar_empty + 8 * slot, ((count >> 1) & 1u) ^ 1u);       // the MMAs that read this slot have retired
+        const uint32_t sbase = smem_base + slot * stage_bytes;
+        const int h = st * kWStageV + v;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float *src = p.X + xoff + (int64_t)rows_next[i] * p.ldX + c4[i];
+          const uint32_t nbytes = rows_next[i] ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + doff[i]), "l"(nbytes ? src : p.X), "r"(nbytes) : "memory");
+        }
+        if (has_g) {
+          const float *gsrc = p.G + (int64_t)min(h, H - 1) * p.ldG + it.np * Np + 32 * g + 16 * half;
+          const uint32_t nbytes = h < H ? 16u : 0u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + 2u * a_bytes + doff[i]), "l"(gsrc + 4 * i), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // advance to the next (item, stage) and prefetch its row indices while the copies fly
+        ++count;
+        if (++st >= it.st_end) {
+          item += (int)gridDim.x;
+          if (item < n_items) { it = w_item(p, item, n_stages, vsplit); st = it.st_begin; setup_item(); }
+        }
+        if (item < n_items) fetch_rows(st, rows_next);
+      }
+      if (pending) {
+        // the previous stage's copies have landed (all but the group just committed)
+        if (issue) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint32_t sbase = smem_base + pend_slot * stage_bytes;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          if (part == 1 && !has_g) break;
+          const uint32_t raw = sbase + (part ? 2u * a_bytes : 0u), small = raw + (part ? g_bytes : a_bytes);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(raw + doff[i]));
+            float4 s;
+            s.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+            s.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            s.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+            s.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small + doff[i]), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async / st.shared data -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) w_mbar_arrive(bar_full + 8 * pend_slot);
+        pending = false;
+      }
+      if (issue) { pending = true; pend_slot = slot; }
+    }
+  } else if (warp == kWMmaWarp) {
+    // ===================== MMA issuer =====================
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *s_tmem, 0);
+    const uint32_t idesc = w_idesc(Np);
+    uint32_t count = 0, cuts = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WItem it = w_item(p, item, n_stages, vsplit);
+      for (int st = it.st_begin; st < it.st_end;) {
+        const uint32_t as = cuts & 1u, aph = (cuts >> 1) & 1u;
+        w_mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem + as * (uint32_t)Np;
+        const int cut_end = min(it.st_end, st + kWCutStages);
+        for (bool first = true; st < cut_end; ++st, ++count) {
+          const uint32_t slot = count & 1u;
+          w_mbar_wait(bar_full + 8 * slot, (count >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sbase = smem_base + slot * stage_bytes;
+          const uint32_t a_raw = sbase, a_small = sbase + a_bytes, g_raw = sbase + 2u * a_bytes, g_small = g_raw + g_bytes;
+#pragma unroll
+          for (int ks = 0; ks < kWStageV / 8; ++ks) {
+            const uint32_t o = (uint32_t)ks * 1024u;
+            w_umma_ss(d, w_desc(a_small + o, 4096u), w_desc(g_raw + o, 4096u), idesc, !(first && ks == 0));
+            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_small + o, 4096u), idesc, 1);
+            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_raw + o, 4096u), idesc, 1);
+          }
+          w_commit(bar_empty + 8 * slot);
+          first = false;
+        }
+        w_commit(bar_acc_full + 8 * as);
+        ++cuts;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                                    // TMEM lane quarter of this warp (warps 9..12 -> 1, 2, 3, 0)
+    const uint32_t pitch_b = (uint32_t)pitch * 4u;
+    const uint32_t tile = sum_base + (uint32_t)(q * 32) * pitch_b;
+    uint32_t cuts = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WItem it = w_item(p, item, n_stages, vsplit);
+      const int n_cut = (it.st_end - it.st_begin + kWCutStages - 1) / kWCutStages;
+      for (int c = 0; c < n_cut; ++c, ++cuts) {
+        const uint32_t as = cuts & 1u, aph = (cuts >> 1) & 1u;
+        const bool last = c == n_cut - 1;
+        w_mbar_wait(bar_acc_full + 8 * as, aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int cb = 0; cb < Np; cb += 32) {
+          float vv[32];
+          w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)Np + cb, vv);
+          const uint32_t my_row = tile + (uint32_t)lane * pitch_b + (uint32_t)cb * 4u;
+          if (c > 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float4 r;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(my_row + (uint32_t)u * 16u));
+              vv[4 * u] += r.x; vv[4 * u + 1] += r.y; vv[4 * u + 2] += r.z; vv[4 * u + 3] += r.w;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)u * 16u), "f"(vv[4 * u]), "f"(vv[4 * u + 1]),
+                         "f"(vv[4 * u + 2]), "f"(vv[4 * u + 3])
+                         : "memory");
+          if (!last) continue;
+          __syncwarp();
+          // transposed read-back: every reduction instruction covers 4 rows x 128 contiguous bytes of dWt
+          const int k_warp = it.kt * kWM + q * 32;
+#pragma unroll
+          for (int it8 = 0; it8 < 8; ++it8) {
+            const int row = it8 * 4 + (lane >> 3);
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(tile + (uint32_t)row * pitch_b + (uint32_t)cb * 4u + (uint32_t)(lane & 7) * 16u));
+            const int k = k_warp + row;
+            if (k < p.K) atomicAdd(reinterpret_cast<float4 *>(p.dWt + (int64_t)k * p.M + it.np * Np + cb + 4 * (lane & 7)), o);
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) w_mbar_arrive(bar_acc_empty + 8 * as);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kWMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+// dbias[m] += sum_h G[h, m]
+__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ G, int64_t ldG, int M, int h_host, const int32_t *h_dev, float *dbias) {
+  __shared__ float s_part[256];
+  const int H = h_dev ? min(*h_dev, h_host) : h_host;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 32 columns x 8 row lanes
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    const int m = m0 + tx;
+    float acc = 0.f;
+    if (m < M)
+      for (int h = blockIdx.x * 8 + ty; h < H; h += gridDim.x * 8) acc += __ldg(G + (int64_t)h * ldG + m);
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0 && m < M) {
+      float tsum = 0.f;
+      for (int r = 0; r < 8; ++r) tsum += s_part[r * 32 + tx];
+      if (tsum != 0.f) atomicAdd(dbias + m, tsum);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace efgh
+
+using namespace efgh;
+
+static size_t wgrad_tc_smem(int Np) {
+  const size_t stage = 2 * 4 * 4096 + 2 * (size_t)(Np / 32) * 4096;
+  return kWStages * stage + (size_t)kWM * (Np + 4) * 4 + 128 + 1024;
+}
+
+extern "C" int efgh_bcl_conv_wgrad_tc_supported(int C, int F, int M) {
+  if (C < 4 || C % 4 != 0 || F < 1 || M < 32 || M > 256 || M % 32 != 0) return 0;
+  if (M > 128 && M % 128 != 0) return 0;
+  return 1;
+}
+
+extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const void *nbr, int idx_bits, int64_t nbr_ld, int F,
+                                      int64_t h, const int32_t *h_dev, const float *dY, int64_t ldY, int M, float *dWt,
+                                      float *dbias, void *stream) {
+  if (!nbr) F = 1;
+  EFGH_REQUIRE(efgh_bcl_conv_wgrad_tc_supported(C, F, M), "efgh_bcl_conv_wgrad_tc: unsupported shape C=%d F=%d M=%d", C, F, M);
+  EFGH_REQUIRE(h >= 0 && h < (1ll << 30), "efgh_bcl_conv_wgrad_tc: bad h");
+  if (h == 0) return EFGH_OK;
+  EFGH_REQUIRE(X && dY && dWt, "efgh_bcl_conv_wgrad_tc: null pointer");
+  EFGH_REQUIRE(ldX % 4 == 0 && ldY % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(dY) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dWt) & 15) == 0,
+               "efgh_bcl_conv_wgrad_tc: X, dY and dWt must be 16-byte aligned with leading dimensions multiple of 4");
+  EFGH_REQUIRE(idx_bits == 32 || idx_bits == 64, "efgh_bcl_conv_wgrad_tc: idx_bits must be 32 or 64");
+  WgradParams p;
+  p.X = X; p.ldX = ldX; p.C = C; p.nbr = nbr; p.nbr_ld = nbr_ld; p.F = F; p.h_host = (int)h; p.h_dev = h_dev;
+  p.G = dY; p.ldG = ldY; p.M = M; p.dWt = dWt; p.K = F * C;
+  p.n_kt = (p.K + kWM - 1) / kWM;
+  p.Np = M > 128 ? 128 : M;
+  p.n_np = M / p.Np;
+  p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
+  const size_t smem = wgrad_tc_smem(p.Np);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = sm_count();
+  if (idx_bits == 32) {
+    auto kern = k_wgrad_tc<int32_t>;
+    EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWThreads, smem, s>>>(p);
+  } else {
+    auto kern = k_wgrad_tc<int64_t>;
+    EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kWThreads, smem, s>>>(p);
+  }
+  EFGH_LAUNCH_CHECK();
+  if (dbias) {
+    k_colsum<<<grid_for(h, 8, 4), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
+    EFGH_LAUNCH_CHECK();
+  }
+  return EFGH_OK;
+}

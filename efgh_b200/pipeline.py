@@ -23,6 +23,7 @@ The ~55 launches and, more importantly, the latency-bound small kernels of the c
 vertices each) are paid once per batch instead of once per scan.
 """
 import functools
+import os
 
 import numpy as np
 import torch
@@ -65,6 +66,7 @@ class ScanPipeline(object):
         self.B = int(batch)
         assert 1 <= self.B <= 64
         self.train = bool(train)
+        self.wgrad_tc = os.environ.get("EFGH_WGRAD", "tc") != "ffma"     # weight gradients on the tensor cores (else the fp32 CUDA-core kernel)
         assert not (train and stem is not None), "training: the stem runs in torch (autograd); pass its output as feat0"
         self.gather_splat = bool(gather_splat)
         self.level0_splat = "vector-atomic scatter + normalise"
@@ -421,15 +423,23 @@ class ScanPipeline(object):
             if self.final_act:
                 ck(L.efgh_bcl_act_bwd(dZl, cout, lv["Z"].data_ptr(), cout, cout, self.final_act, h_cap, h_dev, s), "efgh_bcl_act_bwd")
             ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)          # dZ of this level is complete
-            ck(L.efgh_bcl_conv_wgrad(lv["Y"].data_ptr(), cmid, cmid, None, None, 32, 0, 1, h_cap, h_dev, dZl, cout, None, 0, 0, cout,
-                                     lv["gWt1"].data_ptr(), lv["gb1"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
+            if self.wgrad_tc:
+                ck(L.efgh_bcl_conv_wgrad_tc(lv["Y"].data_ptr(), cmid, cmid, None, 32, 0, 1, h_cap, h_dev, dZl, cout, cout,
+                                            lv["gWt1"].data_ptr(), lv["gb1"].data_ptr(), ss), "efgh_bcl_conv_wgrad_tc")
+            else:
+                ck(L.efgh_bcl_conv_wgrad(lv["Y"].data_ptr(), cmid, cmid, None, None, 32, 0, 1, h_cap, h_dev, dZl, cout, None, 0, 0, cout,
+                                         lv["gWt1"].data_ptr(), lv["gb1"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
             ck(L.efgh_bcl_conv_tc(dZl, cout, cout, None, 0, None, 32, 0, 1, h_cap, h_dev, lv["imgD1"].data_ptr(), None, cmid, 0,
                                   dA1, cmid, self.nsplit, 0, s), "efgh_bcl_conv_tc(dgrad 1x1)")
             ck(L.efgh_bcl_act_bwd(dA1, cmid, lv["Y"].data_ptr(), cmid, cmid, _ACT["relu"], h_cap, h_dev, s), "efgh_bcl_act_bwd")
             # --- conv1
             ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)          # masked dA is complete
-            ck(L.efgh_bcl_conv_wgrad(lv["S"].data_ptr(), cin, cin, None, lv["nbr32"].data_ptr(), 32, h_cap, F, h_cap, h_dev, dA1, cmid,
-                                     None, 0, 0, cmid, lv["gWt0"].data_ptr(), lv["gb0"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
+            if self.wgrad_tc:
+                ck(L.efgh_bcl_conv_wgrad_tc(lv["S"].data_ptr(), cin, cin, lv["nbr32"].data_ptr(), 32, h_cap, F, h_cap, h_dev, dA1, cmid, cmid,
+                                            lv["gWt0"].data_ptr(), lv["gb0"].data_ptr(), ss), "efgh_bcl_conv_wgrad_tc")
+            else:
+                ck(L.efgh_bcl_conv_wgrad(lv["S"].data_ptr(), cin, cin, None, lv["nbr32"].data_ptr(), 32, h_cap, F, h_cap, h_dev, dA1, cmid,
+                                         None, 0, 0, cmid, lv["gWt0"].data_ptr(), lv["gb0"].data_ptr(), ss), "efgh_bcl_conv_wgrad")
             split = lv["splitD0"]
             if split:
                 ck(L.efgh_bcl_zero(None, cg, cg, None, dS + 4 * cg, cg, cg, h_cap, h_dev, 0, s), "efgh_bcl_zero")

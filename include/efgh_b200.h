@@ -281,6 +281,16 @@ int efgh_bcl_conv_wgrad(const float *X, int64_t ldX, int C, const float *row_sca
                         int64_t nbr_ld, int F, int64_t h, const int32_t *h_dev, const float *dY, int64_t ldY,
                         const float *act_out, int64_t ldA, int act, int M, float *dWt, float *dbias, void *stream);
 
+/* Tensor-core variant of efgh_bcl_conv_wgrad (tcgen05 / TMEM, 3xTF32, both operands MN-major in shared memory):
+ *   dWt[(f*C+c), m] += sum_h X[nbr[f,h]+1, c] * dY[h, m];   dbias[m] += sum_h dY[h, m]
+ * dY must already carry the activation mask (efgh_bcl_act_bwd); there is no row_scale.  dWt (and dbias) are accumulated
+ * into: zero-fill first.  efgh_bcl_conv_wgrad_tc_supported: C % 4 == 0 and M in {32, 64, 96, 128, 256}; X, dY, dWt
+ * 16-byte aligned, ldX and ldY multiples of 4. */
+int efgh_bcl_conv_wgrad_tc_supported(int C, int F, int M);
+int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const void *nbr, int idx_bits, int64_t nbr_ld, int F,
+                           int64_t h, const int32_t *h_dev, const float *dY, int64_t ldY, int M, float *dWt, float *dbias,
+                           void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training helpers of the batched pipeline (reference iterater.py:35-43: forward -> loss -> backward).
  *

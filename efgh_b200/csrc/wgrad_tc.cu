@@ -28,12 +28,12 @@ namespace {
 
 constexpr int kWM = 128;                       // conv-k rows per tile (MMA M)
 constexpr int kWStageV = 32;                   // vertices per stage (4 MMA K-steps)
-constexpr int kWStages = 2;
+constexpr int kWMaxStages = 4;                 // ring of stages (as many as shared memory allows: 2 at N = 128, 3 at 64, 4 at 32)
+constexpr int kWTeams = 2;                     // producer teams of 4 warps; team t fills stages t, t+2, ... - two stages are always being gathered
 constexpr int kWCutStages = 8;                 // stages per accumulation chain (256 vertices)
 constexpr int kWProducerWarps = 8;
 constexpr int kWMmaWarp = kWProducerWarps, kWEpiWarp0 = kWProducerWarps + 1;
 constexpr int kWThreads = (kWEpiWarp0 + 4) * 32;   // 416
-constexpr int kWTargetItems = 444;             // ~3 work items per SM
 
 __device__ __forceinline__ uint32_t w_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void w_mbar_init(uint32_t bar, uint32_t count) {
@@ -109,6 +109,7 @@ struct WgradParams {
   const float *G; int64_t ldG; int M;
   float *dWt;                                 // (F*C, M) row-major, accumulated into
   int K, n_kt, n_np, Np;                      // K = F*C; conv-k tiles; output-channel slices of Np columns
+  int ring;                                   // stages in the shared-memory ring
   uint32_t magic_c;
 };
 
@@ -136,23 +137,24 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
   const uint32_t a_bytes = 4u * 4096u;                         // 4 groups x 32 rows x 128 B
   const uint32_t g_bytes = (uint32_t)(Np / 32) * 4096u;
   const uint32_t stage_bytes = 2u * a_bytes + 2u * g_bytes;   // [A raw | A small | G raw | G small]
-  const uint32_t sum_base = smem_base + kWStages * stage_bytes;
+  const uint32_t ring = (uint32_t)p.ring;
+  const uint32_t sum_base = smem_base + ring * stage_bytes;
   const int pitch = Np + 4;                                    // floats per row of the running-sum tile
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWStages * stage_bytes + (size_t)kWM * pitch * 4);
-  // barriers: full[2] empty[2] acc_full[2] acc_empty[2]
-  const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 16, bar_acc_full = bar_full + 32, bar_acc_empty = bar_full + 48;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 8);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)ring * stage_bytes + (size_t)kWM * pitch * 4);
+  // barriers: full[4] empty[4] acc_full[2] acc_empty[2]
+  const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 32, bar_acc_full = bar_full + 64, bar_acc_empty = bar_full + 80;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
   const int n_stages = (H + kWStageV - 1) / kWStageV;
   const int per = p.n_kt * p.n_np;
-  int vsplit = (kWTargetItems + per - 1) / per;
+  int vsplit = (3 * (int)gridDim.x) / per;                    // at most three full rounds of work items (no straggler round)
   vsplit = max(1, min(vsplit, (n_stages + kWCutStages - 1) / kWCutStages));
   const int n_items = n_stages > 0 ? per * vsplit : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWStages; ++s) { w_mbar_init(bar_full + 8 * s, kWProducerWarps); w_mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kWMaxStages; ++s) { w_mbar_init(bar_full + 8 * s, kWProducerWarps / kWTeams); w_mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { w_mbar_init(bar_acc_full + 8 * a, 1); w_mbar_init(bar_acc_empty + 8 * a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -167,102 +169,126 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
 
   if (warp < kWProducerWarps) {
     // ===================== producers =====================
-    const int t = threadIdx.x;
-    const int v = (t >> 1) & 31, g = t >> 6, half = t & 1;
-    const bool has_g = g < Np / 32;
-    // destination offsets of this thread's 4 pieces (16 B each) inside a 32-row group: 32-byte chunks XOR (row & 3)
-    uint32_t doff[4];
+    // Two teams of 128 threads; team t fills stages t, t + 2, ... of the CTA's stage sequence (all stages of item
+    // blockIdx.x, then of item blockIdx.x + gridDim.x, ...).  Warp = 32-wide MN group; a lane copies one 16-byte piece
+    // of 8 vertices' row pieces (gathered rows and dY rows), waits for its OWN copies only, derives the "small" tiles
+    // from what it copied and arrives - no cross-thread dependency inside a stage.
+    const int team = warp / (kWProducerWarps / kWTeams);
+    const int g = warp & 3;                                    // this warp's 32-wide MN group (conv-k / output-channel columns)
+    const int u = lane & 7, vsub = lane >> 3;                  // 8 lanes cooperate on one 128-byte row piece: every LDGSTS instruction
+    const bool has_g = g < Np / 32;                            // covers 4 rows x 128 contiguous bytes (whole cache lines)
+    uint32_t doff[8];                                          // piece u of rows 4 i + vsub: 32-byte chunks XOR (row & 3)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t u = 4u * half + i;
-      doff[i] = (uint32_t)g * 4096u + (uint32_t)v * 128u + ((((u >> 1) ^ ((uint32_t)v & 3u))) << 5) + (u & 1u) * 16u;
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t vr = 4u * i + (uint32_t)vsub;
+      doff[i] = (uint32_t)g * 4096u + vr * 128u + (((((uint32_t)u >> 1) ^ (vr & 3u))) << 5) + ((uint32_t)u & 1u) * 16u;
     }
-    uint32_t count = 0;                                        // stages produced so far (ring position)
-    int rows_next[4];                                          // matrix rows (nbr + 1, 0 = absent) of the stage about to be issued
-    // flattened walk over (item, stage)
-    int item = blockIdx.x;
-    WItem it = item < n_items ? w_item(p, item, n_stages, vsplit) : WItem{0, 0, 0, 0};
-    int st = it.st_begin;
-    int f4[4], c4[4];
-    bool ok4[4];
-    auto setup_item = [&]() {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = it.kt * kWM + 32 * g + 16 * half + 4 * i;
-        ok4[i] = k < p.K;
-        f4[i] = (int)__umulhi((uint32_t)k, p.magic_c);
-        c4[i] = k - f4[i] * p.C;
+
+    // position in the flattened (item, stage) sequence
+    struct Pos { int item, st; WItem it; uint32_t count; };
+    auto pos_valid = [&](const Pos &q) { return q.item < n_items; };
+    auto pos_step = [&](Pos &q) {                              // one stage forward
+      ++q.count;
+      if (++q.st >= q.it.st_end) {
+        q.item += (int)gridDim.x;
+        if (q.item < n_items) { q.it = w_item(p, q.item, n_stages, vsplit); q.st = q.it.st_begin; }
       }
     };
-    auto fetch_rows = [&](int stage, int *rows) {
-      const int h = stage * kWStageV + v;
+    // Neighbour-table entries of this lane's piece for its 8 vertices at position q; the piece lies inside ONE filter
+    // tap (C % 4 == 0), so the lane reads one row of the table.  Eight independent, unconditional loads and NO
+    // arithmetic on their results here: this in-order warp would stall for the L2 latency at the first use (a "+ 1"
+    // right behind each load serialised the eight loads - 5 us per stage); the values are consumed one stage later.
+    auto fetch_rows = [&](const Pos &q, int *raw) {
+      const int k = q.it.kt * kWM + 32 * g + 4 * u;
+      const int f = min((int)__umulhi((uint32_t)k, p.magic_c), p.F - 1);
+      const int h0 = q.st * kWStageV + vsub;
+      if (p.nbr) {
+        const int64_t base = (int64_t)f * p.nbr_ld;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int r = 0;
-        if (h < H && ok4[i]) r = p.nbr ? load_idx<IdxT>(p.nbr, (int64_t)f4[i] * p.nbr_ld + h) + 1 : h + 1;
-        rows[i] = r;
+        for (int i = 0; i < 8; ++i) raw[i] = load_idx<IdxT>(p.nbr, base + min(h0 + 4 * i, H - 1));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = h0 + 4 * i;
       }
     };
-    if (item < n_items) { setup_item(); fetch_rows(st, rows_next); }
+    Pos pi;                                                    // next stage this team issues
+    pi.item = blockIdx.x; pi.count = 0; pi.st = 0;
+    pi.it = pi.item < n_items ? w_item(p, pi.item, n_stages, vsplit) : WItem{0, 0, 0, 0};
+    pi.st = pi.it.st_begin;
+    for (int k = 0; k < team && pos_valid(pi); ++k) pos_step(pi);
+    int rows_next[8];
+    if (pos_valid(pi)) fetch_rows(pi, rows_next);
     const int64_t xoff = p.nbr ? 0 : -(int64_t)p.ldX;          // without a neighbour table X has no sink row: row h+1 -> h
-    bool pending = false;                                      // a stage issued but not yet converted
+    bool pending = false;
     uint32_t pend_slot = 0;
-    while (item < n_items || pending) {
-      uint32_t slot = 0;
-      const bool issue = item < n_items;
-      if (issue) {
-        slot = count & 1u;
-        w_mbar_wait(bar_empty + 8 * slot, ((count >> 1) & 1u) ^ 1u);       // the MMAs that read this slot have retired
-        const uint32_t sbase = smem_base + slot * stage_bytes;
-        const int h = st * kWStageV + v;
+    // landed stage -> "small" tiles -> publish.  keep_newest: the copy group committed last belongs to the NEXT stage
+    auto complete_pending = [&](bool keep_newest) {
+      if (keep_newest) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const uint32_t sbase = smem_base + pend_slot * stage_bytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float *src = p.X + xoff + (int64_t)rows_next[i] * p.ldX + c4[i];
-          const uint32_t nbytes = rows_next[i] ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + doff[i]), "l"(nbytes ? src : p.X), "r"(nbytes) : "memory");
+      for (int part = 0; part < 2; ++part) {
+        if (part == 1 && !has_g) break;
+        const uint32_t raw = sbase + (part ? 2u * a_bytes : 0u), small = raw + (part ? g_bytes : a_bytes);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(raw + doff[i]));
+          float4 sm;
+          sm.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          sm.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          sm.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          sm.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small + doff[i]), "f"(sm.x), "f"(sm.y), "f"(sm.z), "f"(sm.w) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async / st.shared data -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) w_mbar_arrive(bar_full + 8 * pend_slot);
+      pending = false;
+    };
+    // A team's consecutive stages are kWTeams apart in the ring.  With a ring that short (N = 128: two stages) the slot of
+    // the stage to issue is the one still pending, so the pending stage must be published BEFORE waiting for the slot -
+    // otherwise the team would wait for an MMA that waits for the team.
+    const bool serial = ring <= (uint32_t)kWTeams;
+    while (pos_valid(pi) || pending) {
+      const bool issue = pos_valid(pi);
+      if (pending && (serial || !issue)) complete_pending(false);
+      if (issue) {
+        const uint32_t slot = pi.count % ring;
+        w_mbar_wait(bar_empty + 8 * slot, ((pi.count / ring) & 1u) ^ 1u);    // the MMAs that read this slot have retired
+        const uint32_t sbase = smem_base + slot * stage_bytes;
+        const int h0 = pi.st * kWStageV + vsub;
+        const int k = pi.it.kt * kWM + 32 * g + 4 * u;
+        const int f = (int)__umulhi((uint32_t)k, p.magic_c);
+        const float *xc = p.X + xoff + (k - f * p.C);
+        const bool k_ok = k < p.K;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rows_next[i] + 1;                       // matrix row; 0 = absent neighbour (zero-filled)
+          const uint32_t nbytes = (k_ok && h0 + 4 * i < H && row > 0) ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + doff[i]), "l"(nbytes ? xc + (int64_t)row * p.ldX : p.X),
+                       "r"(nbytes)
+                       : "memory");
         }
         if (has_g) {
-          const float *gsrc = p.G + (int64_t)min(h, H - 1) * p.ldG + it.np * Np + 32 * g + 16 * half;
-          const uint32_t nbytes = h < H ? 16u : 0u;
+          const float *gc = p.G + pi.it.np * Np + 32 * g + 4 * u;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + 2u * a_bytes + doff[i]), "l"(gsrc + 4 * i), "r"(nbytes) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // advance to the next (item, stage) and prefetch its row indices while the copies fly
-        ++count;
-        if (++st >= it.st_end) {
-          item += (int)gridDim.x;
-          if (item < n_items) { it = w_item(p, item, n_stages, vsplit); st = it.st_begin; setup_item(); }
-        }
-        if (item < n_items) fetch_rows(st, rows_next);
-      }
-      if (pending) {
-        // the previous stage's copies have landed (all but the group just committed)
-        if (issue) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint32_t sbase = smem_base + pend_slot * stage_bytes;
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          if (part == 1 && !has_g) break;
-          const uint32_t raw = sbase + (part ? 2u * a_bytes : 0u), small = raw + (part ? g_bytes : a_bytes);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(raw + doff[i]));
-            float4 s;
-            s.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-            s.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-            s.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-            s.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small + doff[i]), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+          for (int i = 0; i < 8; ++i) {
+            const int h = h0 + 4 * i;
+            const uint32_t nbytes = h < H ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + 2u * a_bytes + doff[i]), "l"(gc + (int64_t)min(h, H - 1) * p.ldG),
+                         "r"(nbytes)
+                         : "memory");
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async / st.shared data -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) w_mbar_arrive(bar_full + 8 * pend_slot);
-        pending = false;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // this team's next stage: prefetch its row indices while the copies fly
+        for (int k = 0; k < kWTeams && pos_valid(pi); ++k) pos_step(pi);
+        if (pos_valid(pi)) fetch_rows(pi, rows_next);
+        if (pending) complete_pending(true);
+        pending = true;
+        pend_slot = slot;
       }
-      if (issue) { pending = true; pend_slot = slot; }
     }
   } else if (warp == kWMmaWarp) {
     // ===================== MMA issuer =====================
@@ -278,8 +304,8 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
         const uint32_t d = tmem + as * (uint32_t)Np;
         const int cut_end = min(it.st_end, st + kWCutStages);
         for (bool first = true; st < cut_end; ++st, ++count) {
-          const uint32_t slot = count & 1u;
-          w_mbar_wait(bar_full + 8 * slot, (count >> 1) & 1u);
+          const uint32_t slot = count % ring;
+          w_mbar_wait(bar_full + 8 * slot, (count / ring) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = smem_base + slot * stage_bytes;
           const uint32_t a_raw = sbase, a_small = sbase + a_bytes, g_raw = sbase + 2u * a_bytes, g_small = g_raw + g_bytes;
@@ -356,24 +382,32 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
   if (warp == kWMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
-// dbias[m] += sum_h G[h, m]
+// dbias[m] += sum_h G[h, m]: thread = (float4 column group, row lane), rows strided over the grid; one atomic per column
+// and CTA.  HBM-bound: G is read once with 16-byte loads.
 __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ G, int64_t ldG, int M, int h_host, const int32_t *h_dev, float *dbias) {
-  __shared__ float s_part[256];
+  __shared__ float4 s_part[256];
   const int H = h_dev ? min(*h_dev, h_host) : h_host;
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 32 columns x 8 row lanes
-  for (int m0 = 0; m0 < M; m0 += 32) {
-    const int m = m0 + tx;
-    float acc = 0.f;
-    if (m < M)
-      for (int h = blockIdx.x * 8 + ty; h < H; h += gridDim.x * 8) acc += __ldg(G + (int64_t)h * ldG + m);
-    s_part[threadIdx.x] = acc;
-    __syncthreads();
-    if (ty == 0 && m < M) {
-      float tsum = 0.f;
-      for (int r = 0; r < 8; ++r) tsum += s_part[r * 32 + tx];
-      if (tsum != 0.f) atomicAdd(dbias + m, tsum);
+  const int M4 = M >> 2;                                       // <= 64
+  const int lanes = 256 / M4;                                  // row lanes per CTA
+  const int cg = threadIdx.x % M4, rl = threadIdx.x / M4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < lanes) {
+    for (int h = blockIdx.x * lanes + rl; h < H; h += gridDim.x * lanes) {
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(G + (int64_t)h * ldG) + cg);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
     }
-    __syncthreads();
+  }
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int r = 1; r < lanes; ++r) {
+      const float4 q = s_part[r * M4 + cg];
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    if (acc.x != 0.f) atomicAdd(dbias + 4 * cg, acc.x);
+    if (acc.y != 0.f) atomicAdd(dbias + 4 * cg + 1, acc.y);
+    if (acc.z != 0.f) atomicAdd(dbias + 4 * cg + 2, acc.z);
+    if (acc.w != 0.f) atomicAdd(dbias + 4 * cg + 3, acc.w);
   }
 }
 
@@ -382,9 +416,13 @@ __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ G, int
 
 using namespace efgh;
 
-static size_t wgrad_tc_smem(int Np) {
+static size_t wgrad_tc_smem(int Np, int *ring_out) {
   const size_t stage = 2 * 4 * 4096 + 2 * (size_t)(Np / 32) * 4096;
-  return kWStages * stage + (size_t)kWM * (Np + 4) * 4 + 128 + 1024;
+  const size_t fixed = (size_t)kWM * (Np + 4) * 4 + 128 + 1024;
+  int ring = (int)((226 * 1024 - fixed) / stage);
+  if (ring > kWMaxStages) ring = kWMaxStages;
+  if (ring_out) *ring_out = ring;
+  return ring * stage + fixed;
 }
 
 extern "C" int efgh_bcl_conv_wgrad_tc_supported(int C, int F, int M) {
@@ -412,7 +450,8 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
   p.Np = M > 128 ? 128 : M;
   p.n_np = M / p.Np;
   p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
-  const size_t smem = wgrad_tc_smem(p.Np);
+  const size_t smem = wgrad_tc_smem(p.Np, &p.ring);
+  EFGH_REQUIRE(p.ring >= 2, "efgh_bcl_conv_wgrad_tc: no room for two stages");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = sm_count();
   if (idx_bits == 32) {
@@ -426,7 +465,7 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
   }
   EFGH_LAUNCH_CHECK();
   if (dbias) {
-    k_colsum<<<grid_for(h, 8, 4), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
+    k_colsum<<<grid_for(h * (M / 4), 256 * 8, 2), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
     EFGH_LAUNCH_CHECK();
   }
   return EFGH_OK;

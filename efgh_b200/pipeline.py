@@ -158,6 +158,7 @@ class ScanPipeline(object):
                     lv["splitD0"] = self.L.efgh_bcl_conv_tc_groups(F * cmid, cg) > 1
                     offs = [tuple(o) for o in self.gd.radius2offset[radius].tolist()]
                     lv["mirror"] = [offs.index(tuple(-v for v in o)) for o in offs]     # tap f <-> the tap with the negated offset
+                    lv["mirror_t"] = torch.tensor(lv["mirror"], dtype=torch.int64, device=dev)   # (device copy: load_weights may run under graph capture)
                 if self.batch_api:
                     ws_bytes = max(ws_bytes, self.L.efgh_lattice_batch_workspace_bytes(self.B, lv["table"], n_cap))
                 else:
@@ -213,7 +214,7 @@ class ScanPipeline(object):
             if self.train:
                 # conv1's data gradient as a gather over the same neighbour table: dS[g, c] = sum_t sum_m dY[nbr[t,g], m] W0[m, c, mirror(t)]
                 cg = lv["cg"]
-                Wg = W0[:, 4:, :, 0][:, :, lv["mirror"]].permute(2, 0, 1).reshape(F * cmid, cg).contiguous()
+                Wg = W0[:, 4:, :, 0].index_select(2, lv["mirror_t"]).permute(2, 0, 1).reshape(F * cmid, cg).contiguous()
                 ck(L.efgh_bcl_pack_weights(Wg.data_ptr(), F * cmid, cg, self.nsplit, lv["imgD0"].data_ptr(), s), "efgh_bcl_pack_weights")
                 Wd = W1[:, :, 0, 0].contiguous()                        # (K = cout, N = cmid)
                 ck(L.efgh_bcl_pack_weights(Wd.data_ptr(), cout, cmid, self.nsplit, lv["imgD1"].data_ptr(), s), "efgh_bcl_pack_weights")

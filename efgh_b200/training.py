@@ -68,7 +68,7 @@ class BatchedTrainer(object):
     per-scan host work.  (The E-Net head is a per-scan Conv1d / BatchNorm stack outside the lattice path;
     ModulePathTrainer includes it.)"""
 
-    def __init__(self, clouds, dev, world=1, lr=1e-4, seed=0, vertex_cap_factor=2.0, precision="3xtf32"):
+    def __init__(self, clouds, dev, world=1, lr=1e-4, seed=0, vertex_cap_factor=2.0, precision="3xtf32", use_graph=True):
         from .pipeline import ScanPipeline
         torch.manual_seed(seed)
         self.dev, self.world = dev, world
@@ -85,8 +85,12 @@ class BatchedTrainer(object):
             plan = [(m.num_input, list(m.num_output)) for m in self.bcns]
             self.pipe = ScanPipeline(n, synth.SCALE_MAP, plan, self._weights(), dev, vertex_cap_factor=vertex_cap_factor,
                                      emit_int64=False, batch=B, precision=precision, train=True)
+            self._feat0 = torch.empty((plan[0][0] - 4, B * n), dtype=torch.float32, device=dev)   # static input of the captured step
         self.allreduce_calls = 0
         self._checked = False
+        self.use_graph = use_graph
+        self._graph = None
+        self._gstream = None
 
     def _weights(self):
         return [[(c.weight.detach(), c.bias.detach()) for c in m.blur_conv if isinstance(c, nn.Conv2d)] for m in self.bcns]
@@ -94,27 +98,49 @@ class BatchedTrainer(object):
     def parameters(self):
         return self.params
 
+    def _lattice_part(self):
+        """Weight re-layout + lattice build + 5 BCLs forward + loss + backward on this repo's kernels (~130 launches):
+        everything between the stem's forward and its backward.  Reads self._feat0, leaves d feat0 in the pipeline."""
+        pipe = self.pipe
+        pipe.load_weights(self._weights())                 # re-lay the updated weights (device-side, no sync)
+        pipe.enqueue(self.pc, self._feat0)
+        self._loss_dev, dZ = pipe.loss_half_mean_square()   # per-scan means, device-side row counts
+        self._dfeat0 = pipe.backward(dZ)
+
     def step(self):
         pipe = self.pipe
         with torch.cuda.device(self.dev):
             self.opt.zero_grad(set_to_none=True)
-            pipe.load_weights(self._weights())                 # re-lay the updated weights (device-side, no sync)
             feat0 = self.stem(self.pc[None])[0]                # (32, B*n), autograd
-            Z = pipe.enqueue(self.pc, feat0.detach())
-            loss, dZ = pipe.loss_half_mean_square()            # per-scan means, device-side row counts
-            if not self._checked:      # first step only (synchronising): capacities and the symmetry backward() relies on
+            self._feat0.copy_(feat0.detach())
+            if not self._checked:
+                # first step (eager, synchronising once): capacities and the symmetry backward() relies on
+                self._lattice_part()
                 pipe.counts()
                 bad = pipe.aliased_levels()
                 if bad:
                     raise RuntimeError("BatchedTrainer: neighbour tables of levels %s are not mirror-symmetric (aliased keys); "
                                        "use ModulePathTrainer for such clouds" % bad)
                 self._checked = True
-            dfeat0 = pipe.backward(dZ)
-            feat0.backward(dfeat0)
+            elif not self.use_graph:
+                self._lattice_part()
+            else:
+                if self._graph is None:
+                    # capture once (the launch sequence is data-independent: every count stays on the device), then replay:
+                    # one graph launch instead of ~130 kernel launches + ~60 small torch ops per step
+                    self._gstream = torch.cuda.Stream(self.dev)
+                    self._gstream.wait_stream(torch.cuda.current_stream(self.dev))
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self._gstream):
+                        self._lattice_part()
+                    torch.cuda.current_stream(self.dev).wait_stream(self._gstream)
+                    self._graph = g
+                self._graph.replay()
+            feat0.backward(self._dfeat0)
             for m, g in zip(self.bcns, pipe.weight_grads()):
                 convs = [c for c in m.blur_conv if isinstance(c, nn.Conv2d)]
                 for c, (gw, gb) in zip(convs, g):
                     c.weight.grad, c.bias.grad = gw, gb
             self.allreduce_calls = sharding.allreduce_gradients(self.params, self.world)
             self.opt.step()
-        return loss
+        return self._loss_dev

@@ -25,7 +25,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
   return ((uint64_t)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(128) k_probe(const float *A, const float *G, float *D, int variant) {
+__global__ void __launch_bounds__(128) k_probe(const float *A, const float *G, float *D, int variant, int reps, unsigned long long *ns) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
@@ -72,14 +72,16 @@ __global__ void __launch_bounds__(128) k_probe(const float *A, const float *G, f
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
-  if (tid == 0) {
+  unsigned long long t0 = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (tid == 0) for (int rep = 0; rep < reps; ++rep) {
     // kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), N = 64, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(MK >> 4) << 24);
     const uint32_t group_stride = V * 128, kstep_stride = 8 * 128, katom_stride = 4 * 128;
     for (int s = 0; s < V / 8 && variant == 2; ++s) {
       const uint32_t idk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(MK >> 4) << 24);
       const uint64_t da = make_desc(a_base + s * 32, 16, 1024), dg = make_desc(g_base + s * 32, 16, 1024);
-      const uint32_t acc = s > 0;
+      const uint32_t acc = s > 0 || rep > 0;
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da),
                    "l"(dg), "r"(idk), "r"(acc)
                    : "memory");
@@ -87,15 +89,16 @@ __global__ void __launch_bounds__(128) k_probe(const float *A, const float *G, f
     for (int s = 0; s < V / 8 && variant != 2; ++s) {
       const uint32_t lbo = variant == 0 ? group_stride : katom_stride, sbo = variant == 0 ? katom_stride : group_stride;
       const uint64_t da = make_desc(a_base + s * kstep_stride, lbo, sbo, 1u), dg = make_desc(g_base + s * kstep_stride, lbo, sbo, 1u);
-      const uint32_t acc = s > 0;
+      const uint32_t acc = s > 0 || rep > 0;
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da),
                    "l"(dg), "r"(idesc), "r"(acc)
                    : "memory");
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    if (rep == reps - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
   asm volatile("{\n\t.reg .pred p;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0, 20000;\n\t@p bra Dn;\n\tbra W;\n\tDn:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); *ns = t1 - t0; }
   for (int cb = 0; cb < NN; cb += 32) {
     uint32_t r[32];
     asm volatile(
@@ -132,7 +135,8 @@ int main() {
   CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int variant = 0; variant < 3; ++variant) {
     CK(cudaMemset(dD, 0, D.size() * 4));
-    k_probe<<<1, 128, smem>>>(dA, dG, dD, variant);
+    unsigned long long *dns; CK(cudaMalloc(&dns, 8));
+    k_probe<<<1, 128, smem>>>(dA, dG, dD, variant, 1, dns);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("variant %d: CUDA error %s\n", variant, cudaGetErrorString(e)); return 1; }
     CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
@@ -140,6 +144,14 @@ int main() {
     for (size_t i = 0; i < D.size(); ++i) { double d = fabs((double)D[i] - Dref[i]); if (d > maxerr) maxerr = d; bad += d != 0; }
     printf("variant %d (LBO = %s stride): max abs err %.4f, %d of %zu wrong; D[0][0..3] = %.2f %.2f %.2f %.2f  ref %.2f %.2f %.2f %.2f\n", variant,
            variant == 0 ? "MN-group" : variant == 1 ? "K-group" : "(K-major sanity)", maxerr, bad, D.size(), D[0], D[1], D[2], D[3], Dref[0], Dref[1], Dref[2], Dref[3]);
+  }
+  for (int variant = 0; variant < 3; variant += 2) {
+    unsigned long long *dns, hns; CK(cudaMalloc(&dns, 8));
+    const int reps = 2000;
+    k_probe<<<1, 128, smem>>>(dA, dG, dD, variant, reps, dns);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&hns, dns, 8, cudaMemcpyDeviceToHost));
+    printf("%s operands: %d MMAs (M=128, N=%d, K=8) in %llu ns = %.1f ns per MMA\n", variant == 0 ? "MN-major" : "K-major", reps * V / 8, NN, hns, (double)hns / (reps * V / 8));
   }
   return 0;
 }

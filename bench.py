@@ -298,7 +298,11 @@ def stage_model(pipe, counts, n_points):
         idx = 12 if pipe.emit_int64 else 4
         out["L%d.points" % li] = (12 * n + 32 * n, 0)
         out["L%d.vertices" % li] = (4 * idx * n + F * idx * H + (12 * H if lv["next"] is not None else 0), 0)
-        feat_in = (12 * n if li == 0 and pipe.stem is not None else 4 * (cin - 4) * n)
+        if li == 0 and getattr(pipe, "gs0", False):            # stem (or transpose) writes point-major rows, the splat gathers them
+            out["L0.stem"] = (12 * n + 4 * (cin - 4) * n, 2.0 * n * (3 * 32 + 32 * 32 + 32 * 32) if pipe.stem is not None else 0)
+            feat_in = 4 * (cin - 4) * n
+        else:
+            feat_in = (12 * n if li == 0 and pipe.stem is not None else 4 * (cin - 4) * n)
         out["L%d.splat" % li] = (feat_in + 48 * n + 4 * cin * (H + 1), 0)
         wbytes = 4 * F * cin * cmid * (2 if pipe.nsplit == 3 else 1)
         out["L%d.conv1" % li] = (4 * cin * (H + 1) + 4 * F * H + 4 * cmid * H + wbytes, 2.0 * H * F * cin * cmid)
@@ -307,7 +311,7 @@ def stage_model(pipe, counts, n_points):
     return out
 
 
-KERNEL_STAGE = (("k_clear", None), ("k_points", "points"), ("k_assign", "points"), ("k_vertices", "vertices"), ("k_zero", "zero"),
+KERNEL_STAGE = (("k_stem_rows", "stem"), ("k_clear", None), ("k_points", "points"), ("k_assign", "points"), ("k_vertices", "vertices"), ("k_zero", "zero"),
                 ("k_scatter", "splat"), ("k_normalize", "splat"), ("k_splat", "splat"), ("k_conv_tc", "conv"), ("k_conv", "conv"))
 
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "efgh_bcl_scatter": (i32, [vp, i64, i64, i32, vp, i64, i64, i32, i64, vp, vp, i64, vp, i32, i64, i32, vp, i64, vp, vp]),
     "efgh_bcl_stem_weight_floats": (i64, [i32, i32, i32, i32]),
     "efgh_bcl_scatter_stem": (i32, [vp, i64, i64, i32, vp, i64, i32, i32, i32, i32, vp, f32, i64, vp, vp, i64, vp, i32, i64, i32, vp, i64, vp, vp]),
+    "efgh_bcl_stem_rows": (i32, [vp, i64, i32, i32, i32, i32, vp, f32, i64, vp, vp, i64, vp]),
     "efgh_bcl_splat_gather": (i32, [vp, vp, i64, i32, vp, vp, i64, vp, i32, vp, i64, vp, vp]),
     "efgh_bcl_zero": (i32, [vp, i64, i32, vp, vp, i64, i32, i64, vp, i32, vp]),
     "efgh_bcl_inv_norm": (i32, [vp, vp, i64, vp, i32, vp]),

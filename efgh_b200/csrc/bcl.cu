@@ -154,6 +154,74 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const 
   }
 }
 
+// ---- stem as a kernel of its own --------------------------------------------------------------------------------------
+// The gather-form splat (below) wants its per-point features as point-major rows.  For level 0 those are E-Net's stem
+// features (reference nets/enet.py:24-28,111): one thread evaluates the three pointwise layers of ONE point entirely
+// in registers - weights are read from shared memory as broadcast 16-byte loads (transposed [k][o], zero-padded to
+// 32 x 32 so that every loop has a compile-time trip count and the activations stay in registers) - and writes the
+// point's 32 features as one 128-byte row.  Same accumulation order as the fused variant in k_scatter (bias first,
+// input channels ascending, fmaf).
+__global__ void __launch_bounds__(128)
+k_stem_rows(Stem stem, int n_host, const int32_t *n_dev, float *__restrict__ out, int64_t out_ld) {
+  __shared__ __align__(16) float s_w[3][32 * 32 + 32];          // per layer: Wt[k][o] (32 x 32, zero padded), then bias[32]
+  for (int i = threadIdx.x; i < 3 * (32 * 32 + 32); i += blockDim.x) (&s_w[0][0])[i] = 0.f;
+  __syncthreads();
+  {
+    int base = 0;
+    const int cins[3] = {stem.cin, stem.c1, stem.c2}, couts[3] = {stem.c1, stem.c2, stem.c3};
+    for (int l = 0; l < 3; ++l) {
+      const int ci = cins[l], co = couts[l];
+      for (int i = threadIdx.x; i < ci * co; i += blockDim.x) {
+        const int o = i / ci, k = i - o * ci;
+        s_w[l][k * 32 + o] = __ldg(stem.w + base + i);
+      }
+      for (int i = threadIdx.x; i < co; i += blockDim.x) s_w[l][32 * 32 + i] = __ldg(stem.w + base + ci * co + i);
+      base += ci * co + co;
+    }
+  }
+  __syncthreads();
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  const float slope = stem.slope;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float a[32], b[32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = k < stem.cin ? __ldg(stem.pts + k * stem.pts_ld + i) : 0.f;
+    // layer 1 (cin <= 4 inputs)
+#pragma unroll
+    for (int o4 = 0; o4 < 8; ++o4) {
+      float4 acc = *reinterpret_cast<const float4 *>(&s_w[0][32 * 32 + 4 * o4]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w = *reinterpret_cast<const float4 *>(&s_w[0][k * 32 + 4 * o4]);
+        acc.x = fmaf(w.x, a[k], acc.x); acc.y = fmaf(w.y, a[k], acc.y); acc.z = fmaf(w.z, a[k], acc.z); acc.w = fmaf(w.w, a[k], acc.w);
+      }
+      b[4 * o4] = acc.x > 0.f ? acc.x : slope * acc.x; b[4 * o4 + 1] = acc.y > 0.f ? acc.y : slope * acc.y;
+      b[4 * o4 + 2] = acc.z > 0.f ? acc.z : slope * acc.z; b[4 * o4 + 3] = acc.w > 0.f ? acc.w : slope * acc.w;
+    }
+    // layers 2 and 3 (<= 32 inputs each): b -> a -> b
+#pragma unroll
+    for (int l = 1; l < 3; ++l) {
+      float *in = l == 1 ? b : a, *o = l == 1 ? a : b;
+#pragma unroll
+      for (int o4 = 0; o4 < 8; ++o4) {
+        float4 acc = *reinterpret_cast<const float4 *>(&s_w[l][32 * 32 + 4 * o4]);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float4 w = *reinterpret_cast<const float4 *>(&s_w[l][k * 32 + 4 * o4]);
+          acc.x = fmaf(w.x, in[k], acc.x); acc.y = fmaf(w.y, in[k], acc.y); acc.z = fmaf(w.z, in[k], acc.z); acc.w = fmaf(w.w, in[k], acc.w);
+        }
+        o[4 * o4] = acc.x > 0.f ? acc.x : slope * acc.x; o[4 * o4 + 1] = acc.y > 0.f ? acc.y : slope * acc.y;
+        o[4 * o4 + 2] = acc.z > 0.f ? acc.z : slope * acc.z; o[4 * o4 + 3] = acc.w > 0.f ? acc.w : slope * acc.w;
+      }
+    }
+    float4 *row = reinterpret_cast<float4 *>(out + (int64_t)i * out_ld);
+    const int c34 = stem.c3 >> 2;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < c34) row[q] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+  }
+}
+
 // ---- gather-form splat ---------------------------------------------------------------------------------------------
 // The atomic splat above is bound by the L2's atomic units (~150 G red.v4/s measured) and every lattice vertex
 // receives 5 - 20 contributions.  With the vertex -> contributions lists the lattice build can emit
@@ -164,8 +232,8 @@ k_scatter(const float *__restrict__ feat, int64_t sc, int64_t sn, int C1, const 
 // zero-fill of S, the atomics and the normalisation pass.  The level's own 4 el_minus_gr channels and the 4
 // barycentric weights of a point come from ONE 32-byte sector (point_rows).  Vertices with more than kHeavy
 // contributions (coincident points) are listed by the lattice build and get a whole CTA.
-constexpr int kSplatHeavy = 128;      // == lattice.cu kHeavy
-constexpr int kSplatMaxHeavy = 1024;  // == lattice.cu kMaxHeavy
+constexpr int kSplatHeavy = 64;        // == lattice.cu kHeavy
+constexpr int kSplatMaxHeavy = 16384;  // == lattice.cu kMaxHeavy
 
 template <int NV, int LPR>
 struct SplatAcc {
@@ -902,6 +970,21 @@ extern "C" int efgh_bcl_scatter_stem(const float *feat, int64_t stride_c, int64_
   Stem st = {pts, pts_ld, stem_weights, c_in, c1, c2, c3, leaky_slope};
   return scatter_impl("efgh_bcl_scatter_stem", feat, stride_c, stride_n, C, nullptr, 0, 0, c3, n, n_dev, w, w_ld, off, idx_bits,
                       off_ld, row_shift, S, ldS, wsum, st, stream);
+}
+
+extern "C" int efgh_bcl_stem_rows(const float *pts, int64_t pts_ld, int c_in, int c1, int c2, int c3, const float *stem_weights,
+                                  float leaky_slope, int64_t n, const int32_t *n_dev, float *out, int64_t out_ld, void *stream) {
+  EFGH_REQUIRE(pts && stem_weights && out && pts_ld >= n, "efgh_bcl_stem_rows: null pointer or pts_ld < n");
+  EFGH_REQUIRE(c_in >= 1 && c_in <= 4 && c1 >= 4 && c1 <= 32 && c2 >= 4 && c2 <= 32 && c3 >= 4 && c3 <= 32 && c1 % 4 == 0 &&
+                   c2 % 4 == 0 && c3 % 4 == 0,
+               "efgh_bcl_stem_rows: stem widths %d -> %d -> %d -> %d (inputs <= 4, layers multiples of 4 up to 32)", c_in, c1, c2, c3);
+  EFGH_REQUIRE(n >= 0 && n < (1ll << 30) && out_ld >= c3 && out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "efgh_bcl_stem_rows: bad sizes or unaligned output");
+  if (n == 0) return EFGH_OK;
+  Stem st = {pts, pts_ld, stem_weights, c_in, c1, c2, c3, leaky_slope};
+  k_stem_rows<<<grid_for(n, 128, 16), 128, 0, static_cast<cudaStream_t>(stream)>>>(st, (int)n, n_dev, out, out_ld);
+  EFGH_LAUNCH_CHECK();
+  return EFGH_OK;
 }
 
 extern "C" int efgh_bcl_splat_gather(const float *point_rows, const float *feat2, int64_t stride_n2, int C2,

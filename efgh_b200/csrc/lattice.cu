@@ -65,10 +65,12 @@ struct Batch {
   float *point_rows;         // optional (n, 8) point-major copy: el_minus_gr[0..3], barycentric[0..3]
   int h_cap;
 };
-// A vertex with more than kHeavy contributions (coincident points, e.g. returns clipped to the range box) is listed so
-// that the gather-form splat can put a whole CTA on it instead of one warp.
-constexpr int kHeavy = 128;
-constexpr int kMaxHeavy = 1024;
+// A vertex with more than kHeavy contributions is listed so that the gather-form splat can put a whole CTA on it instead
+// of a few lanes.  At level 0 those are common: the ground rings next to the sensor put 50-100 points into one lattice
+// cell (a 16-scan batch lists a few thousand vertices); an overflowing list makes single lanes walk lists of several
+// hundred contributions serially - measured 4x on the whole level-0 splat.
+constexpr int kHeavy = 64;
+constexpr int kMaxHeavy = 16384;
 inline int batch_tm_off(int B) { return (B + 1 + 7) & ~7; }
 inline int batch_box_off(int B) { return batch_tm_off(B) + ((B + 7) & ~7); }
 
@@ -294,6 +296,13 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
       pr[1] = make_float4(b[0], b[1], b[2], b[3]);
     }
 
+    // key box of the point's 4 keys (generate_data.py:135-136): over the remainders r = 0..3 coordinate c takes the values
+    // greedy[c] + canonical[rank[c]][r] = greedy[c] + {-rank[c], ..., 3 - rank[c]}
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      kmin[c] = min(kmin[c], gi[c] - rank[c]);
+      kmax[c] = max(kmax[c], gi[c] + 3 - rank[c]);
+    }
     int s4[4];
     unsigned long long key4[4], cur4[4];
     unsigned h4[4];
@@ -301,11 +310,7 @@ k_points(const float *__restrict__ pts, int64_t pts_ld, float scale, float *__re
     for (int r = 0; r < 4; ++r) {                            // :106 keys[c, n, r] = greedy[c] + canonical[rank[c], r]
       int k[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        k[c] = gi[c] + canonical(rank[c], r);
-        kmin[c] = min(kmin[c], k[c]);
-        kmax[c] = max(kmax[c], k[c]);
-      }
+      for (int c = 0; c < 4; ++c) k[c] = gi[c] + canonical(rank[c], r);
       key4[r] = pack_key(k[0], k[1], k[2]);
       h4[r] = hash_key(key4[r]) & mask;
     }

@@ -46,14 +46,19 @@ def _on_own_device(fn):
 class ScanPipeline(object):
     def __init__(self, n_points, scales_filter_map, bcl_plan, weights, device, stem_channels=32,
                  vertex_cap_factor=1.0, emit_int64=True, last_relu=False, use_leaky=True, use_norm=True,
-                 precision="3xtf32", batch=1, gather_splat=True, stem=None, train=False):
+                 precision="3xtf32", batch=1, gather_splat=True, stem=None, train=False, level0_gather=None):
         """bcl_plan: [(C_in, [C_mid, C_out]), ...] one entry per level (reference nets/enet.py:30-83);
         weights: per level [(W0 (C_mid,C_in,F,1), b0), (W1 (C_out,C_mid,1,1), b1)] torch tensors;
         vertex_cap_factor: capacity of every vertex-side buffer as a multiple of n_points;
         precision: "3xtf32" (tcgen05, fp32-equivalent), "tf32" (tcgen05, one pass) or "fp32" (CUDA cores);
         gather_splat: levels >= 1 (whose input features are the previous level's point-major output rows) splat
         through the vertex -> contributions lists of the lattice build - no atomics, zero-fill and normalisation
-        fused.  Level 0 (channel-major (C, N) input, working set beyond the L2 in batch mode) keeps the atomic scatter;
+        fused;
+        level0_gather: level 0 the same way, from point-major (N, C_stem) feature rows that efgh_bcl_stem_rows computes
+        from the cloud (stem given) or that are transposed from feat0.  Off by default = vector-atomic scatter of the
+        channel-major (C, N) input (stem evaluated on the scatter's tile) + normalisation pass: measured on 16-scan
+        batches (r2) the gather form's splat is faster (667 vs ~740 us) but materialising the 268 MB of feature rows
+        and building level 0's contribution lists costs more than that saves (1 190 vs 930 us in total);
         stem: None, or ([(W1, b1), (W2, b2), (W3, b3)], use_leaky) - E-Net's pointwise `conv_in` (reference
         nets/enet.py:24-28; W as Conv1d weights (out, in, 1)): the level-0 splat then COMPUTES the stem features from
         the cloud (SURVEY.md §8 f1) and enqueue() ignores feat0;
@@ -69,7 +74,6 @@ class ScanPipeline(object):
         self.wgrad_tc = os.environ.get("EFGH_WGRAD", "tc") != "ffma"     # weight gradients on the tensor cores (else the fp32 CUDA-core kernel)
         assert not (train and stem is not None), "training: the stem runs in torch (autograd); pass its output as feat0"
         self.gather_splat = bool(gather_splat)
-        self.level0_splat = "vector-atomic scatter + normalise"
         self.stem = None
         if stem is not None:
             layers, leaky = stem
@@ -79,6 +83,9 @@ class ScanPipeline(object):
             flat = torch.cat([t.detach().to(torch.float32).reshape(-1) for W, b in layers for t in (W, b)])
             assert flat.numel() == self.L.efgh_bcl_stem_weight_floats(*dims)
             self.stem = {"dims": dims, "w": flat.to(self.dev).contiguous(), "slope": 0.1 if leaky else 0.0}
+        self.gs0 = self.gather_splat and bool(level0_gather)
+        self.level0_splat = ("gather through vertex -> contributions lists from point-major stem rows" if self.gs0
+                             else "vector-atomic scatter + normalise")
         self.batch_api = self.B > 1 or self.gather_splat       # the batch entry points also serve a batch of one
         self.n_scan = int(n_points)
         self.n0 = int(n_points) * self.B
@@ -116,12 +123,12 @@ class ScanPipeline(object):
                     # one scan's hash table: 4 x its vertex capacity (load factor <= 0.25), never more than 8 per point.
                     # The tables of a whole batch should stay in the 126 MB L2 (8 scans x 8 MB); at 2 x capacity
                     # (load ~0.4) the longer probe sequences were measured to cost more than the footprint saves.
-                    "table": int(self.L.efgh_lattice_table_entries(n_cap_scan, 2 * cap_scan)),
+                    "table": int(self.L.efgh_lattice_table_entries(n_cap_scan, int(float(os.environ.get("EFGH_TABLE_FACTOR", "2")) * cap_scan))),
                     "info": torch.zeros(max(int(self.L.efgh_lattice_batch_info_ints(self.B)), 1), dtype=i32, device=dev),
-                    "gs": self.gather_splat and li > 0,
-                    "voff": torch.zeros(int(self.L.efgh_lattice_vertex_offsets_ints(h_cap)), dtype=i32, device=dev) if self.gather_splat and li > 0 else None,
-                    "prow": torch.zeros((n_cap, 8), dtype=f32, device=dev) if self.gather_splat and li > 0 else None,
-                    "contrib": torch.zeros(4 * n_cap, dtype=i32, device=dev) if self.gather_splat and li > 0 else None,
+                    "gs": self.gather_splat and (li > 0 or self.gs0),
+                    "voff": torch.zeros(int(self.L.efgh_lattice_vertex_offsets_ints(h_cap)), dtype=i32, device=dev) if self.gather_splat and (li > 0 or self.gs0) else None,
+                    "prow": torch.zeros((n_cap, 8), dtype=f32, device=dev) if self.gather_splat and (li > 0 or self.gs0) else None,
+                    "contrib": torch.zeros(4 * n_cap, dtype=i32, device=dev) if self.gather_splat and (li > 0 or self.gs0) else None,
                     "n_cap": n_cap, "h_cap": h_cap, "F": F, "scale": float(scale), "cin": cin, "cmid": cmid, "cout": cout,
                     "divisor": float(np.float32(self.gd.expected_std * scale)),
                     "offs": torch.from_numpy(self.gd.radius2offset[radius].astype(np.int32)).to(dev),
@@ -188,6 +195,7 @@ class ScanPipeline(object):
             self.scan_start = torch.tensor(self._starts0, dtype=i32, device=dev)
             self._pc_dev = torch.empty((3, self.n0), dtype=f32, device=dev)
             self._feat_dev = torch.empty((stem_channels, self.n0), dtype=f32, device=dev)
+            self._feat_rows = torch.empty((self.n0, stem_channels), dtype=f32, device=dev) if self.gs0 else None   # point-major level-0 features
         # per launch sequence: clear/points/assign, vertices, zero, splat (+ normalise | level-0 transpose), conv1, conv2
         self.launches_per_scan = self.nlev * (3 + 1 + 1 + 1 + 2) + sum(0 if lv["gs"] else 1 for lv in self.levels)
 
@@ -273,6 +281,18 @@ class ScanPipeline(object):
             prev_ptr, prev_sc, prev_sn, prev_c = None, 0, 1, self.stem["dims"][3]
         else:
             prev_ptr, prev_sc, prev_sn, prev_c = feat0.data_ptr(), feat0.stride(0), 1, feat0.shape[0]
+        if self.gs0:
+            # level-0 features as point-major rows (on the BCL stream: overlaps the lattice build of level 0)
+            def rows0():
+                if self.stem is not None:
+                    d = self.stem["dims"]
+                    ck(L.efgh_bcl_stem_rows(pc.data_ptr(), pc.stride(0), d[0], d[1], d[2], d[3], self.stem["w"].data_ptr(), self.stem["slope"],
+                                            self.n0, None, self._feat_rows.data_ptr(), self._feat_rows.stride(0), s), "efgh_bcl_stem_rows")
+                else:
+                    with torch.cuda.stream(main):
+                        self._feat_rows.copy_(feat0.t())
+            timed("L0.stem", rows0)
+            prev_ptr, prev_sc, prev_sn, prev_c = self._feat_rows.data_ptr(), 1, self._feat_rows.stride(0), self._feat_rows.shape[1]
         n_dev = None
         seg = self.scan_start.data_ptr()                      # batched: point-stream boundaries of the level
         if self.batch_api:

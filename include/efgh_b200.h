@@ -176,6 +176,12 @@ int efgh_bcl_scatter_stem(const float *feat, int64_t stride_c, int64_t stride_n,
                           const int32_t *n_dev, const float *w, int64_t w_ld, const void *off, int idx_bits,
                           int64_t off_ld, int row_shift, float *S, int64_t ldS, float *wsum, void *stream);
 
+/* E-Net's pointwise stem as a kernel of its own (reference nets/enet.py:24-28,111, nets/net_utils.py:35-43): writes the
+ * (n, c3) POINT-MAJOR feature rows (row stride out_ld) that efgh_bcl_splat_gather reads at level 0; weights packed as
+ * for efgh_bcl_scatter_stem. */
+int efgh_bcl_stem_rows(const float *pts, int64_t pts_ld, int c_in, int c1, int c2, int c3, const float *stem_weights,
+                       float leaky_slope, int64_t n, const int32_t *n_dev, float *out, int64_t out_ld, void *stream);
+
 /* Gather-form splat + density normalisation in one pass (reference nets/bilateralNN.py:176-211, with E-Net's input
  * wiring `cat(el_minus_gr, previous features)`, reference nets/enet.py:113-137): for every vertex h
  *   S[h+1, :] = (sum over its contributions (point i, remainder r) of bary[r,i] * [el_minus_gr[:, i] ; feat2[i, :]]) * inv,

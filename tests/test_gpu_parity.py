@@ -286,8 +286,9 @@ def test_batched_forward_host_matches_enqueue(dev):
         assert H.rel_err(out.numpy(), want_Z.numpy()) < 1e-6          # same kernels; only the atomics' order differs
 
 
+@pytest.mark.parametrize("l0_gather", [False, True])
 @pytest.mark.parametrize("name,batch", [("leaky", 1), ("relu", 1), ("leaky", 3)])
-def test_fused_stem_pipeline(name, batch, dev, golden_dir):
+def test_fused_stem_pipeline(name, batch, l0_gather, dev, golden_dir):
     """E-Net's pointwise stem computed inside the level-0 splat.  Level-0 BCL output with the stem fused
     (only the cloud goes in) must match the float64 oracle fed with the reference-golden stem weights:
     oracle stem -> cat(el_minus_gr, stem) -> oracle BCL, within the per-layer tolerance."""
@@ -301,7 +302,10 @@ def test_fused_stem_pipeline(name, batch, dev, golden_dir):
     n = 16384
     clouds = [synth.synth_scan(50 + b, "os1-64-16k") for b in range(batch)]
     weights = make_enet_weights(synth.ENET_BCL, seed=4)
-    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=batch, stem=(layers, leaky))
+    # l0_gather: the stem as a kernel of its own writing point-major rows + gather-form splat at level 0 as well
+    pipe = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=4.0, batch=batch, stem=(layers, leaky),
+                        level0_gather=l0_gather)
+    assert pipe.gs0 == l0_gather
     pc_all = torch.from_numpy(np.concatenate(clouds, axis=1)).to(dev)
     for _ in range(2):
         pipe.enqueue(pc_all, None)

@@ -18,7 +18,7 @@ def main():
     dev = torch.device("cuda:0")
     scans = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     clouds = [torch.from_numpy(synth.synth_scan(i, "os1-64-64k")).to(dev) for i in range(scans)]
-    tr = training.BatchedTrainer(clouds, dev)
+    tr = training.BatchedTrainer(clouds, dev, use_graph=False)     # eager launches: ncu lists every kernel of the step
     with torch.no_grad():
         for p in tr.params:
             p.normal_(0, 0.1 if p.dim() > 1 else 0.05)

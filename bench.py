@@ -90,8 +90,9 @@ def workload_config(args, train):
                 "sensor": TRAIN_SENSOR, "points_per_scan": n, "levels": len(synth.SCALE_MAP),
                 "l2_policy": "working set larger than L2: one step streams > 1 GB of lattice / feature / gradient buffers"}
     n = synth.SENSORS[args.sensor][0] * synth.SENSORS[args.sensor][1]
-    return {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd%s"
-                        % (args.sensor, n, "" if args.no_stem else ", stem fused (input = cloud only)"),
+    return {"workload": "configs[1]: %s scans (%d pts), 5-level lattice build + 5 E-Net BCL fwd (value: cloud + stem features resident in "
+                        "HBM; e2e: %s)" % (args.sensor, n, "cloud + features from pinned host memory" if args.no_stem else
+                                           "cloud only from pinned host memory, E-Net stem fused into the level-0 splat"),
             "sensor": args.sensor, "points_per_scan": n, "levels": len(synth.SCALE_MAP),
             "l2_policy": "working set larger than L2: every launch sequence streams > 1 GB of lattice / feature buffers; "
                          "%d distinct scans resident per GPU, cycled" % args.resident}
@@ -315,7 +316,7 @@ KERNEL_STAGE = (("k_stem_rows", "stem"), ("k_clear", None), ("k_points", "points
                 ("k_scatter", "splat"), ("k_normalize", "splat"), ("k_splat", "splat"), ("k_conv_tc", "conv"), ("k_conv", "conv"))
 
 
-def ncu_sequence_traffic(args, timeout=240):
+def ncu_sequence_traffic(args, zero_levels=None, timeout=240):
     """DRAM bytes of every kernel of ONE eager launch sequence, measured now with an ncu metrics pass over
     tools/ncu_sequence.py (same pipeline configuration as the bench).  Returns ({stage: bytes}, note)."""
     ncu = None
@@ -332,7 +333,7 @@ def ncu_sequence_traffic(args, timeout=240):
         log = os.path.join(td, "seq.csv")
         cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
                "--csv", "--log-file", log, sys.executable, os.path.join(ROOT, "tools", "ncu_sequence.py"), "--scan-batch", str(args.scan_batch),
-               "--sensor", args.sensor] + (["--no-stem"] if args.no_stem else []) + (["--int32-only"] if args.int32_only else []) + \
+               "--sensor", args.sensor, "--no-stem"] + (["--int32-only"] if args.int32_only else []) + \
               (["--atomic-splat"] if args.atomic_splat else [])
         env = dict(os.environ)
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
@@ -370,6 +371,8 @@ def ncu_sequence_traffic(args, timeout=240):
             lvl, st = k // 2, "conv%d" % (1 + k % 2)
         elif pat in ("k_scatter", "k_normalize"):
             lvl = 0
+        elif pat == "k_zero" and zero_levels:
+            lvl = zero_levels[k] if k < len(zero_levels) else k
         elif pat == "k_splat":
             lvl = k + (0 if "k_scatter" not in seen else 1)
         else:
@@ -468,6 +471,8 @@ def run_ours(args):
         l0 = _capi.lib().efgh_launch_count()
         ms = timed_region(lambda: tr.step(), steps)
         launches = int(_capi.lib().efgh_launch_count() - l0)     # this library's kernels (torch's own stem / optimizer kernels not counted)
+        if getattr(tr, "_graph", None) is not None:               # replayed CUDA graph: the captured launches run again every step
+            launches = int(tr.launches_per_step * steps)
         # end to end: the step's inputs come from pinned host memory, the loss goes back to the host, every step
         pins = [torch.from_numpy(c).pin_memory() for c in host]
         loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
@@ -540,10 +545,14 @@ def run_ours(args):
                              gather_splat=not args.atomic_splat, stem=(stem_layers, True) if stem_on else None,
                              emit_int64=not args.int32_only) for _ in range(count)]
 
-    feats = None if use_stem else make_feats()
+    # `value` leg = the metric's path as BASELINE.json states it: lattice build + 5 BCL forward, its inputs (cloud and the
+    # (32, N) stem features that reference nets/enet.py:111 feeds bcn1) resident in HBM.  The e2e leg goes through the
+    # public API from what a caller has - the cloud (reference nets/enet.py:103-111) - with the stem fused into the
+    # level-0 splat (`--no-stem`: the features come from the host as well).
+    feats = make_feats()
     pc_dev = [torch.from_numpy(np.concatenate(clouds[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NR)]
-    ft_dev = [None] * NR if use_stem else [torch.from_numpy(np.concatenate(feats[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NR)]
-    pipes = make_pipes(use_stem, NP)
+    ft_dev = [torch.from_numpy(np.concatenate(feats[g * G:(g + 1) * G], axis=1)).to(dev) for g in range(NR)]
+    pipes = make_pipes(False, NP)
     streams = [torch.cuda.Stream(dev) for _ in range(P)]
     copy_streams = [torch.cuda.Stream(dev) for _ in range(NP)]
     use_graph = not args.no_graph
@@ -616,7 +625,23 @@ def run_ours(args):
         return {"value": B * world * steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     e2e_steps = max(2, args.steps // 2)
-    e2e = e2e_leg(pipes, use_stem, feats, e2e_steps)
+    pipes_stem = make_pipes(True, NP) if use_stem else None
+    e2e = e2e_leg(pipes_stem if use_stem else pipes, use_stem, feats, e2e_steps)
+    value_stem = None
+    if use_stem:      # the stem-fused pipeline with the clouds resident: what the extra stem work costs on the device
+        gr = [pipes_stem[j % NP].graph_for(pc_dev[j], None, streams[j % P]) for j in range(NR)] if use_graph else None
+
+        def step_stem():
+            for i in range(NG):
+                j = i % NR
+                if use_graph:
+                    with torch.cuda.stream(streams[j % P]):
+                        gr[j].replay()
+                else:
+                    pipes_stem[j % NP].enqueue(pc_dev[j], None, stream=streams[j % P])
+        step_stem()
+        vsteps = max(2, args.steps // 4)
+        value_stem = B * world * vsteps / (timed_region(step_stem, vsteps, streams + copy_streams) * 1e-3)
 
     # ---- per-stage table: eager launches with CUDA events on the launching stream (events cannot be read back from
     #      inside a replayed graph), three passes over resident group 0, median
@@ -632,10 +657,10 @@ def run_ours(args):
 
     # ---- single-scan latency (one scan per launch sequence, CUDA graph)
     pipe1 = pipes[0] if G == 1 else ScanPipeline(N, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=1.0,
-                                                 gather_splat=not args.atomic_splat, stem=(stem_layers, True) if use_stem else None)
+                                                 gather_splat=not args.atomic_splat)
     lat = []
     pc1_dev = pc_dev[0][:, :N].contiguous()
-    ft1_dev = ft_dev[0][:, :N].contiguous() if not use_stem else None
+    ft1_dev = ft_dev[0][:, :N].contiguous()
     g1 = pipe1.graph_for(pc1_dev, ft1_dev, streams[0]) if use_graph else None
     for _ in range(7):
         torch.cuda.synchronize(dev)
@@ -655,13 +680,11 @@ def run_ours(args):
     extras = {}
     if not args.no_extras:
         try:   # the other input variant: the (32, N) stem features come from the host as well (18.4 MB per scan)
-            alt_feats = feats if feats is not None else make_feats()
-            alt = make_pipes(not use_stem, NP)
+            alt = pipes if use_stem else make_pipes(True, NP)
             alt_steps = max(2, e2e_steps // 4)
             extras["e2e_variants"] = {
                 "stem_fused_cloud_only" if use_stem else "stem_features_from_host": e2e,
-                "stem_features_from_host" if use_stem else "stem_fused_cloud_only": e2e_leg(alt, not use_stem, alt_feats, alt_steps)}
-            del alt
+                "stem_features_from_host" if use_stem else "stem_fused_cloud_only": e2e_leg(alt, not use_stem, feats, alt_steps)}
         except Exception as e:
             extras["e2e_variants"] = {"error": repr(e)}
         try:
@@ -688,7 +711,8 @@ def run_ours(args):
     model = stage_model(pipes[0], counts, N * G)
     tf32_peak = tf32_peak_tflops(torch, dev)
     traffic, traffic_note = (None, "skipped (--no-extras)") if args.no_extras else \
-        ((None, "not measured at N > 1 (ncu never wraps a multi-rank command)") if world > 1 else ncu_sequence_traffic(args))
+        ((None, "not measured at N > 1 (ncu never wraps a multi-rank command)") if world > 1 else
+         ncu_sequence_traffic(args, [li for li, lv in enumerate(pipes[0].levels) if (not lv["gs"]) or (lv["tc"] and lv.get("split0"))]))
     mma_mult = 3.0 if pipes[0].nsplit == 3 else 1.0
     levels = []
     for li in range(nlev):
@@ -733,7 +757,7 @@ def run_ours(args):
                     "lattice_index_dtype": "int64 (reference format) + int32 copies for the BCL kernels" if pipes[0].emit_int64 else "int32 only",
                     "conv_precision": pipes[0].precision, "cuda_graphs": use_graph, "single_scan_latency_ms": float(np.median(lat)),
                     "algorithmic_MB_per_scan": total_bytes / 1e6, "scan_roofline_frac": total_bytes / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                    "e2e_over_value": e2e["value"] / value, "numa": numa, "tf32_peak_tflops_measured": tf32_peak,
+                    "e2e_over_value": e2e["value"] / value, "value_stem_fused_resident_cloud": value_stem, "numa": numa, "tf32_peak_tflops_measured": tf32_peak,
                     "timed_region_s": ms * 1e-3},
         "roofline_levels": levels,
         "stages_us": stages,          # per launch sequence (G scans), eager single-stream pass

@@ -310,7 +310,11 @@ struct TeamPos {
   }
 };
 
-template <typename IdxT, int NSPLIT>
+// COMBINE: an item's contraction is cut into several accumulation chains that the epilogue sums in shared memory.  A
+// compile-time switch: without it (one chain per item - 1x1 convolutions, K groups added in L2) the epilogue keeps its
+// constant-pitch staging tile and the MMA issuer its per-item loop; every instruction either executes per item gates the
+// other roles (measured: the run-time version cost the short 1x1 convolutions 35 %).
+template <typename IdxT, int NSPLIT, bool COMBINE>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [B ring: b_stages x (B_big | B_small?)] [raw ring: raw_slots x 512 threads x 128 B] [epilogue staging] [barriers]
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
   const uint32_t b_bytes = (uint32_t)N * 128u * (NSPLIT == 3 ? 2 : 1);
   const uint32_t raw_base = smem_base + (uint32_t)p.b_stages * b_bytes;
   const uint32_t epi_base = raw_base + (uint32_t)p.raw_slots * kRawSlotBytes;   // 4 epilogue warps x 32 rows x epi_pitch floats
-  const int epi_pitch = p.cut_chunks > 0 ? N + 4 : kEpiRowFloats;               // on-chip cuts: the whole 128 x N running sum lives here
+  const int epi_pitch = COMBINE ? N + 4 : kEpiRowFloats;                        // on-chip cuts: the whole 128 x N running sum lives here
   float *s_bias = reinterpret_cast<float *>(smem + (size_t)p.b_stages * b_bytes + (size_t)p.raw_slots * kRawSlotBytes + (size_t)(4 * 32 * 4) * epi_pitch);
   float *s_in_bias = s_bias + 256;
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + kBiasFloats);
@@ -348,6 +352,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     int gbeg = p.n_chunks, gend;
     if (i < p.n_groups) group_range(p.n_chunks, p.n_groups, i, gbeg, gend);
     s_gb[i] = gbeg;
+  }
+  int *s_cut = s_gb + kMaxGroups + 4 + kProducerWarps * 64;    // COMBINE: [0] number of cuts, [1 + c] first chunk of cut c (last entry: n_chunks)
+  if (COMBINE && threadIdx.x == 0) {
+    const int n_cut = max(1, (p.n_chunks + p.cut_chunks - 1) / p.cut_chunks);
+    s_cut[0] = n_cut;
+    for (int c = 0; c <= n_cut; ++c) {
+      int b, e;
+      group_range(p.n_chunks, n_cut, min(c, n_cut - 1), b, e);
+      s_cut[1 + c] = c < n_cut ? b : p.n_chunks;
+    }
   }
   const int it_dq = (int)gridDim.x / p.n_groups, it_dr = (int)gridDim.x % p.n_groups;   // item += gridDim.x in (tile, group) terms
   for (int i = threadIdx.x; i < N; i += kThreads) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -563,11 +577,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int gi = item % p.n_groups;
         const int i_begin = s_gb[gi], i_end = s_gb[gi + 1];
-        const int n_cut = p.cut_chunks > 0 ? max(1, (i_end - i_begin + p.cut_chunks - 1) / p.cut_chunks) : 1;
+        const int n_cut = COMBINE ? s_cut[0] : 1;              // (COMBINE runs with one K group: every item has the same cuts)
         for (int c = 0; c < n_cut; ++c, ++tcount) {
-        int j_begin, j_end;
-        group_range(i_end - i_begin, n_cut, c, j_begin, j_end);
-        j_begin += i_begin; j_end += i_begin;
+        const int j_begin = COMBINE ? s_cut[1 + c] : i_begin, j_end = COMBINE ? s_cut[2 + c] : i_end;
         const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
         const uint32_t aph = p.acc_stages == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
         if (lane == 0) trace_ev(p.trace, 3, ntrace, 100 + (int)tcount);
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
     const uint32_t stage = epi_base + (uint32_t)(warp - kEpiWarp0) * (32u * pitch_b);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int tile = item / p.n_groups, gi = item - tile * p.n_groups;
-      const int n_cut = p.cut_chunks > 0 ? max(1, (s_gb[gi + 1] - s_gb[gi] + p.cut_chunks - 1) / p.cut_chunks) : 1;
+      const int n_cut = COMBINE ? s_cut[0] : 1;
       const int h_warp = tile * kTileM + q * 32;
       for (int c = 0; c < n_cut; ++c, ++tcount) {
       const uint32_t as = p.acc_stages == 2 ? (tcount & 1) : 0;
@@ -656,8 +668,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
         if (tracer) trace_ev(p.trace, 4, ntrace, 10);
-        const uint32_t my_row = stage + (uint32_t)lane * pitch_b + (p.cut_chunks > 0 ? (uint32_t)cb * 4u : 0u);
-        if (c > 0) {                                          // running sum of the earlier cuts of this tile
+        const uint32_t my_row = stage + (uint32_t)lane * pitch_b + (COMBINE ? (uint32_t)cb * 4u : 0u);
+        if (COMBINE && c > 0) {                               // running sum of the earlier cuts of this tile
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             float4 r;
@@ -670,14 +682,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)u * 16u),
                        "f"(v[4 * u]), "f"(v[4 * u + 1]), "f"(v[4 * u + 2]), "f"(v[4 * u + 3])
                        : "memory");
-        if (!last) continue;
+        if (COMBINE && !last) continue;
         // bias of the 4 columns this lane will store after the transposition (one 16-byte load per block)
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!p.accumulate) bv = *(reinterpret_cast<const float4 *>(s_bias + cb) + (lane & 7));
         __syncwarp();
         if (tracer) trace_ev(p.trace, 4, ntrace, 11);
         float4 o[8];
-        const uint32_t blk = stage + (p.cut_chunks > 0 ? (uint32_t)cb * 4u : 0u);
+        const uint32_t blk = stage + (COMBINE ? (uint32_t)cb * 4u : 0u);
 #pragma unroll
         for (int it8 = 0; it8 < 8; ++it8) {                   // all shared loads first, then all global stores: one warp cannot hide
           const int row = it8 * 4 + (lane >> 3);              // the load latency of an interleaved load/store sequence
@@ -782,7 +794,7 @@ constexpr int kOnChipMaxN = 128;
 
 // Resource plan for output width N: TMEM = acc_stages*N + 4 teams x (32|64) A columns <= 512;
 // shared memory = b_stages weight tiles + raw_slots x 64 KB of warp-private row slots + the epilogue tile.
-static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
+static bool conv_tc_plan(int N, int nsplit, bool combine, ConvParams *p, size_t *smem_out) {
   const int a_cols = nsplit == 3 ? 64 : 32;
   const int room = 512 - kTeams * a_cols;                // TMEM columns left for accumulators
   int nacc = 1, acc_stages = 1;
@@ -793,8 +805,8 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
   else if (2 * N <= room) { nacc = 1; acc_stages = 2; }
   if (acc_stages * nacc * N > room) return false;
   const size_t b_bytes = (size_t)N * 128 * (nsplit == 3 ? 2 : 1);
-  const size_t epi_bytes = (size_t)4 * 32 * 4 * (N <= kOnChipMaxN ? N + 4 : kEpiRowFloats);
-  const size_t fixed = 1024 + 256 + (kMaxGroups + 4) * 4 + kProducerWarps * 256 + epi_bytes + kBiasFloats * 4;
+  const size_t epi_bytes = (size_t)4 * 32 * 4 * (combine ? N + 4 : kEpiRowFloats);
+  const size_t fixed = 1024 + 256 + (kMaxGroups + 4) * 4 + kProducerWarps * 256 + 256 /* cut table */ + epi_bytes + kBiasFloats * 4;
   const size_t budget = 226 * 1024 - fixed;
   int b_stages = b_bytes >= 32 * 1024 ? 2 : 4;
   if ((size_t)b_stages * b_bytes + kRawSlotBytes > budget) return false;
@@ -808,7 +820,7 @@ static bool conv_tc_plan(int N, int nsplit, ConvParams *p, size_t *smem_out) {
 extern "C" int efgh_bcl_conv_tc_supported(int C, int F, int M, int nsplit) {
   if (!(nsplit == 1 || nsplit == 3)) return 0;
   if (C < 32 || C > 512 || C % 4 != 0 || M < 32 || M > 256 || M % 32 != 0 || F < 1) return 0;
-  return conv_tc_plan(M, nsplit, nullptr, nullptr) ? 1 : 0;
+  return conv_tc_plan(M, nsplit, M <= kOnChipMaxN, nullptr, nullptr) ? 1 : 0;
 }
 
 extern "C" size_t efgh_bcl_packed_weight_bytes(int K, int M, int nsplit) {
@@ -868,23 +880,27 @@ extern "C" int efgh_bcl_conv_tc(const float *X, int64_t ldX, int C, const float 
   EFGH_REQUIRE(accumulate || p.n_groups == 1,
                "efgh_bcl_conv_tc: K=%d needs %d partial sums; call with accumulate=1 on a zero-filled Y", F * C, p.n_groups);
   EFGH_REQUIRE(ldX < (1ll << 30), "efgh_bcl_conv_tc: ldX too large");   // row pitch in bytes fits 32 bits; mad.wide.u32 gives the 64-bit offset
+  const bool combine = p.cut_chunks > 0 && p.n_chunks > p.cut_chunks;     // more than one accumulation chain per item
+  EFGH_REQUIRE(!combine || (p.n_chunks + p.cut_chunks - 1) / p.cut_chunks <= 60, "efgh_bcl_conv_tc: K=%d too long for on-chip chain cuts", F * C);
   size_t smem = 0;
-  conv_tc_plan(M, nsplit, &p, &smem);
+  conv_tc_plan(M, nsplit, combine, &p, &smem);
   if ((g_conv_flags >> 4) & 15) p.raw_slots = min(p.raw_slots, (g_conv_flags >> 4) & 15);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t items = ((h + kTileM - 1) / kTileM) * p.n_groups;
   const int grid = (int)(items < sm_count() ? items : sm_count());
-#define EFGH_LAUNCH_TC(IDX, NS)                                                                                   \
+#define EFGH_LAUNCH_TC(IDX, NS, CB)                                                                               \
   do {                                                                                                            \
-    auto kern = k_conv_tc<IDX, NS>;                                                                               \
+    auto kern = k_conv_tc<IDX, NS, CB>;                                                                           \
     EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<grid, kThreads, smem, s>>>(p);                                                                         \
   } while (0)
+#define EFGH_LAUNCH_TC2(IDX, NS) do { if (combine) EFGH_LAUNCH_TC(IDX, NS, true); else EFGH_LAUNCH_TC(IDX, NS, false); } while (0)
   if (idx_bits == 32) {
-    if (nsplit == 3) EFGH_LAUNCH_TC(int32_t, 3); else EFGH_LAUNCH_TC(int32_t, 1);
+    if (nsplit == 3) EFGH_LAUNCH_TC2(int32_t, 3); else EFGH_LAUNCH_TC2(int32_t, 1);
   } else {
-    if (nsplit == 3) EFGH_LAUNCH_TC(int64_t, 3); else EFGH_LAUNCH_TC(int64_t, 1);
+    if (nsplit == 3) EFGH_LAUNCH_TC2(int64_t, 3); else EFGH_LAUNCH_TC2(int64_t, 1);
   }
+#undef EFGH_LAUNCH_TC2
 #undef EFGH_LAUNCH_TC
   EFGH_LAUNCH_CHECK();
   return EFGH_OK;

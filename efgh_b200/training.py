@@ -91,6 +91,7 @@ class BatchedTrainer(object):
         self.use_graph = use_graph
         self._graph = None
         self._gstream = None
+        self.launches_per_step = 0
 
     def _weights(self):
         return [[(c.weight.detach(), c.bias.detach()) for c in m.blur_conv if isinstance(c, nn.Conv2d)] for m in self.bcns]
@@ -115,7 +116,10 @@ class BatchedTrainer(object):
             self._feat0.copy_(feat0.detach())
             if not self._checked:
                 # first step (eager, synchronising once): capacities and the symmetry backward() relies on
+                from . import _capi
+                l0 = _capi.lib().efgh_launch_count()
                 self._lattice_part()
+                self.launches_per_step = int(_capi.lib().efgh_launch_count() - l0)   # this library's kernels in one step (a replayed graph re-launches them)
                 pipe.counts()
                 bad = pipe.aliased_levels()
                 if bad:

@@ -731,19 +731,34 @@ def run_ours(args):
     dom = max((k for k in stages if k in model), key=lambda k: stages[k])
     dom_bytes, dom_flops = model[dom]
     dom_ms = stages[dom] * 1e-3
-    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
     total_bytes, _ = pipes[0].algorithmic_bytes(counts)
     total_bytes /= G                                    # per scan
     scan_ms = ms / (B * args.steps)
-    roof = {"kernel": "%s (%d scans per launch)" % (dom, G), "bound": "hbm",
-            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-            "traffic": traffic.get(dom) if traffic else None, "traffic_source": traffic_note,
-            "peak_source": peaks["source"] + " copy bandwidth (MEASURED_PEAKS.json)" if peaks["source"] == "measured" else "fallback",
-            "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
-            "tensor_tflops_fp32_equiv": dom_flops / (dom_ms * 1e-3) / 1e12 if dom_flops else None,
-            "share_of_scan": stages[dom] / max(sum(stages.values()), 1e-9),
-            "note": "timed with CUDA events on the launching stream over three eager passes (median); see roofline_levels for the "
-                    "convolutions' tensor-pipe fractions against the cuBLAS TF32 peak measured in this run (%.0f TFLOP/s)" % tf32_peak}
+    # which ceiling bounds the dominant kernel: the lower one of its two roofline times - algorithmic bytes at the
+    # measured copy bandwidth, or the tensor-pipe work it issues (3 MMAs per product with 3xTF32) at the cuBLAS TF32
+    # rate measured in this run
+    t_hbm = dom_bytes / (peaks["hbm_gbs"] * 1e9)
+    t_tensor = dom_flops * mma_mult / (tf32_peak * 1e12) if dom_flops else 0.0
+    if t_tensor > t_hbm:
+        ach = dom_flops * mma_mult / (dom_ms * 1e-3) / 1e12
+        roof = {"kernel": "%s (%d scans per launch)" % (dom, G), "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": ach / tf32_peak,
+                "peak_source": "cuBLAS TF32 GEMM (torch.matmul fp32, allow_tf32, 8192^3, best of 5) measured in this run - MEASURED_PEAKS.json "
+                               "holds only a bf16 figure (%.0f TFLOP/s), TF32 runs at half of that nominally" % peaks["bf16_tflops"],
+                "hbm_frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    else:
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roof = {"kernel": "%s (%d scans per launch)" % (dom, G), "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"],
+                "peak_source": peaks["source"] + " copy bandwidth (MEASURED_PEAKS.json)" if peaks["source"] == "measured" else "fallback"}
+    roof.update({"traffic": traffic.get(dom) if traffic else None, "traffic_source": traffic_note,
+                 "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
+                 "tensor_tflops_fp32_equiv": dom_flops / (dom_ms * 1e-3) / 1e12 if dom_flops else None,
+                 "share_of_scan": stages[dom] / max(sum(stages.values()), 1e-9),
+                 "limiter": next((l["bound"] for l in levels if l["stage"] == dom), None),
+                 "note": "timed with CUDA events on the launching stream over three eager passes (median); `limiter` is what the kernel "
+                         "is short of in practice (issue = instruction issue / gather rate, profiles/r2_conv_tc_levels.json); "
+                         "roofline_levels lists every convolution"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

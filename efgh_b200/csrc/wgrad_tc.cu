@@ -465,7 +465,7 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
   }
   EFGH_LAUNCH_CHECK();
   if (dbias) {
-    k_colsum<<<grid_for(h * (M / 4), 256 * 8, 2), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
+    k_colsum<<<grid_for(h * (M / 4), 256 * 4, 8), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
     EFGH_LAUNCH_CHECK();
   }
   return EFGH_OK;

@@ -10,6 +10,11 @@
 //
 // Lattice-side matrices are vertex-major (row = vertex, C contiguous floats) so one neighbour is one
 // contiguous 4*C-byte read and a splat contribution is a handful of 16-byte vector reductions.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace efgh {
@@ -219,6 +224,142 @@ k_stem_rows(Stem stem, int n_host, const int32_t *n_dev, float *__restrict__ out
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (q < c34) row[q] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+  }
+}
+
+// ---- warp-private splat (level 0) -----------------------------------------------------------------------------------
+// The tile kernel above spends its time between CTA barriers: load tile -> __syncthreads -> atomics -> __syncthreads, with
+// four scalar shared-memory loads and a division per vector atomic; it reaches ~125-150 G red.v4/s where the hardware
+// sustains ~320 G/s into a destination that is L2-resident (tools/bulk_reduce_probe.cu: 16 scans' 230 MB matrix at
+// random 126 G/s, <= 115 MB 313 G/s - and the splat walks the batch scan by scan, so one scan's 14.5 MB is what is hot).
+// Here every WARP owns its 32-point tile: lane = point for the coalesced channel-major loads (or for the stem, computed
+// in registers), the point's C floats go to a warp-private POINT-major shared-memory row with 16-byte stores, and after
+// one __syncwarp the warp issues the tile's 4 * 32 * C/4 vector atomics - one 16-byte shared load, four multiplies, one
+// red.v4 each; nine consecutive lanes cover one 144-byte row of S.  No CTA-wide barrier anywhere in the loop.
+// C4T: C / 4 at compile time (9 for E-Net's level 0; 0 = run-time value).
+__device__ __forceinline__ void stem_eval_point(const float (*s_w)[32 * 32 + 32], const Stem &stem, int i, float *b) {
+  float a[32];
+  const float slope = stem.slope;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = k < stem.cin ? __ldg(stem.pts + k * stem.pts_ld + i) : 0.f;
+#pragma unroll
+  for (int o4 = 0; o4 < 8; ++o4) {
+    float4 acc = *reinterpret_cast<const float4 *>(&s_w[0][32 * 32 + 4 * o4]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 w = *reinterpret_cast<const float4 *>(&s_w[0][k * 32 + 4 * o4]);
+      acc.x = fmaf(w.x, a[k], acc.x); acc.y = fmaf(w.y, a[k], acc.y); acc.z = fmaf(w.z, a[k], acc.z); acc.w = fmaf(w.w, a[k], acc.w);
+    }
+    b[4 * o4] = acc.x > 0.f ? acc.x : slope * acc.x; b[4 * o4 + 1] = acc.y > 0.f ? acc.y : slope * acc.y;
+    b[4 * o4 + 2] = acc.z > 0.f ? acc.z : slope * acc.z; b[4 * o4 + 3] = acc.w > 0.f ? acc.w : slope * acc.w;
+  }
+#pragma unroll
+  for (int l = 1; l < 3; ++l) {
+    float *in = l == 1 ? b : a, *o = l == 1 ? a : b;
+#pragma unroll
+    for (int o4 = 0; o4 < 8; ++o4) {
+      float4 acc = *reinterpret_cast<const float4 *>(&s_w[l][32 * 32 + 4 * o4]);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float4 w = *reinterpret_cast<const float4 *>(&s_w[l][k * 32 + 4 * o4]);
+        acc.x = fmaf(w.x, in[k], acc.x); acc.y = fmaf(w.y, in[k], acc.y); acc.z = fmaf(w.z, in[k], acc.z); acc.w = fmaf(w.w, in[k], acc.w);
+      }
+      o[4 * o4] = acc.x > 0.f ? acc.x : slope * acc.x; o[4 * o4 + 1] = acc.y > 0.f ? acc.y : slope * acc.y;
+      o[4 * o4 + 2] = acc.z > 0.f ? acc.z : slope * acc.z; o[4 * o4 + 3] = acc.w > 0.f ? acc.w : slope * acc.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void stem_load_weights(float (*s_w)[32 * 32 + 32], const Stem &stem) {
+  for (int i = threadIdx.x; i < 3 * (32 * 32 + 32); i += blockDim.x) (&s_w[0][0])[i] = 0.f;
+  __syncthreads();
+  int base = 0;
+  const int cins[3] = {stem.cin, stem.c1, stem.c2}, couts[3] = {stem.c1, stem.c2, stem.c3};
+  for (int l = 0; l < 3; ++l) {
+    const int ci = cins[l], co = couts[l];
+    for (int i = threadIdx.x; i < ci * co; i += blockDim.x) {
+      const int o = i / ci, k = i - o * ci;
+      s_w[l][k * 32 + o] = __ldg(stem.w + base + i);
+    }
+    for (int i = threadIdx.x; i < co; i += blockDim.x) s_w[l][32 * 32 + i] = __ldg(stem.w + base + ci * co + i);
+    base += ci * co + co;
+  }
+  __syncthreads();
+}
+
+template <typename IdxT, int C4T, bool STEM>
+__global__ void __launch_bounds__(STEM ? 128 : 256)
+k_scatter_warp(const float *__restrict__ feat, int64_t sc, int C1, const float *__restrict__ feat2, int64_t sc2, int C2, int n_host,
+               const int32_t *n_dev, const float *__restrict__ w, int64_t w_ld, const void *__restrict__ off, int64_t off_ld,
+               int shift, float *S, int64_t ldS, float *wsum, Stem stem) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = C1 + C2, C4 = C4T ? C4T : C >> 2;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // per warp: tile [32 points][C] | weights [4][32] | rows [4][32]
+  const int warp_floats = 32 * C + 256;
+  float *tile = smem + (size_t)wid * warp_floats;
+  float *s_w = tile + 32 * C;
+  int *s_row = reinterpret_cast<int *>(s_w + 128);
+  float (*s_stem)[32 * 32 + 32] = reinterpret_cast<float (*)[32 * 32 + 32]>(smem + (size_t)nw * warp_floats);
+  if (STEM) stem_load_weights(s_stem, stem);
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  const int n_tiles = (n + 31) >> 5;
+  const int warps = gridDim.x * nw;
+  for (int t = blockIdx.x * nw + wid; t < n_tiles; t += warps) {
+    const int i = t * 32 + lane;
+    const bool ok = i < n;
+    const int np = min(32, n - t * 32);
+    float4 *my = reinterpret_cast<float4 *>(tile + lane * C);
+    // ---- the point's C channels -> its shared-memory row (16-byte stores: conflict-free at a 144-byte pitch)
+    for (int q = 0; q < (C1 >> 2); ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) { v.x = __ldg(feat + (4 * q) * sc + i); v.y = __ldg(feat + (4 * q + 1) * sc + i); v.z = __ldg(feat + (4 * q + 2) * sc + i); v.w = __ldg(feat + (4 * q + 3) * sc + i); }
+      my[q] = v;
+    }
+    if (STEM) {
+      float b[32];
+      stem_eval_point(s_stem, stem, ok ? i : 0, b);
+      const int c34 = stem.c3 >> 2;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < c34) my[(C1 >> 2) + q] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+    } else {
+      for (int q0 = 0; q0 < (C2 >> 2); q0 += 4) {              // 16 independent loads in flight per lane
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && q < (C2 >> 2)) {
+            v[u].x = __ldg(feat2 + (4 * q) * sc2 + i); v[u].y = __ldg(feat2 + (4 * q + 1) * sc2 + i);
+            v[u].z = __ldg(feat2 + (4 * q + 2) * sc2 + i); v[u].w = __ldg(feat2 + (4 * q + 3) * sc2 + i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + u < (C2 >> 2)) my[(C1 >> 2) + q0 + u] = v[u];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      s_w[r * 32 + lane] = ok ? __ldg(w + r * w_ld + i) : 0.f;
+      s_row[r * 32 + lane] = ok ? load_idx<IdxT>(off, r * off_ld + i) + shift : -1;
+    }
+    __syncwarp();
+    // ---- the tile's vector atomics: item = (point, remainder, 16-byte piece), pieces of one row on consecutive lanes
+    const int items = np * 4 * C4;
+    for (int it = lane; it < items; it += 32) {
+      const int pr = it / C4, c4 = it - pr * C4;
+      const int r = pr & 3, pt = pr >> 2;
+      const int row = s_row[r * 32 + pt];
+      if (row < 0) continue;
+      const float wt = s_w[r * 32 + pt];
+      float4 v = *reinterpret_cast<const float4 *>(tile + pt * C + 4 * c4);
+      v.x *= wt; v.y *= wt; v.z *= wt; v.w *= wt;
+      atomicAdd(reinterpret_cast<float4 *>(S + (int64_t)row * ldS) + c4, v);
+      if (wsum && c4 == 0) atomicAdd(wsum + row, wt);
+    }
+    __syncwarp();
   }
 }
 
@@ -928,10 +1069,38 @@ int scatter_impl(const char *who, const float *feat, int64_t stride_c, int64_t s
   // (four times as many CTAs - the deep levels have few points)
   const bool wide = stem.pts ? true : (C >= C2 ? stride_n == 1 : stride_n2 == 1);   // layout of the wider source decides
   const int TP = wide ? 32 : 8;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Channel-major sources, 16-byte rows: the warp-private kernel (no CTA barriers in the loop).  EFGH_SCATTER=tile
+  // keeps the tile kernel (timing studies).
+  static const bool tile_only = getenv("EFGH_SCATTER") && !strcmp(getenv("EFGH_SCATTER"), "tile");
+  const int Ct = C + C2;
+  static const bool warp_always = getenv("EFGH_SCATTER") && !strcmp(getenv("EFGH_SCATTER"), "warp");
+  // (measured, 16 scans per launch: with the stem fused the warp-private kernel makes the whole sequence 3.4 % faster; with
+  //  the features read from memory its level-0 stage is 10 % faster stand-alone but the CUDA-graph replay, where the next
+  //  level's lattice kernels run beside it, 7 % slower than with the tile kernel - so it is the default for the stem only)
+  if (!tile_only && (stem.pts || warp_always) && stride_n == 1 && (stem.pts || C2 == 0 || stride_n2 == 1) && C % 4 == 0 && C2 % 4 == 0 && Ct <= 128 && ldS % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (!stem.pts || stem.c3 == C2)) {
+    const int threads = stem.pts ? 128 : 256, nw = threads / 32;
+    const size_t smem_w = sizeof(float) * ((size_t)nw * (32 * Ct + 256) + (stem.pts ? 3 * (32 * 32 + 32) : 0));
+    int per_sm = (int)std::min<size_t>(stem.pts ? 4 : 8, (200 * 1024) / smem_w);
+    if (getenv("EFGH_SCATTER_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("EFGH_SCATTER_CTAS"))));   // timing studies
+    EFGH_REQUIRE(per_sm >= 1, "%s: C=%d too large", who, Ct);
+    return dispatch_idx(idx_bits, [&](auto tag) -> int {
+      using IdxT = decltype(tag);
+      auto launch = [&](auto kern) -> int {
+        if (smem_w > 48 * 1024) EFGH_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        kern<<<grid_for((n + 31) / 32, nw, per_sm), threads, smem_w, s>>>(feat, stride_c, C, feat2, stride_c2, C2, (int)n, n_dev, w, w_ld, off, off_ld,
+                                                                          row_shift, S, ldS, wsum, stem);
+        EFGH_LAUNCH_CHECK();
+        return EFGH_OK;
+      };
+      if (stem.pts) return Ct == 36 ? launch(k_scatter_warp<IdxT, 9, true>) : launch(k_scatter_warp<IdxT, 0, true>);
+      return Ct == 36 ? launch(k_scatter_warp<IdxT, 9, false>) : launch(k_scatter_warp<IdxT, 0, false>);
+    });
+  }
   size_t smem = sizeof(float) * ((size_t)(C + C2) * (TP + 1) + 4 * TP) + sizeof(int) * 4 * TP;
   if (stem.pts) smem += sizeof(float) * (stem_weight_floats(stem.cin, stem.c1, stem.c2, stem.c3) + (4 + 64) * (TP + 1));
   EFGH_REQUIRE(smem <= 200 * 1024, "%s: C=%d too large", who, C + C2);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dispatch_idx(idx_bits, [&](auto tag) -> int {
     using IdxT = decltype(tag);
     auto launch = [&](auto kern) -> int {

@@ -21,17 +21,28 @@
 //               of a work item the 128 x N tile is added to dWt in global memory (red.add, one per vertex split)
 // Work item = (128-wide conv-k tile, 128-wide slice of the output channels, vertex range); the vertex count is read
 // from device memory and split so that all SMs have work.
+#include <stdlib.h>
+
 #include "common.cuh"
+
+// Timing-study switches (tools/wgrad_tc_time.py; results are WRONG with any of them set):
+//   bit 0  the MMA issuer issues only the first MMA pair of a stage      bit 1  producers skip the "small" tiles
+//   bit 2  producers skip the copies                                     bit 3  the epilogue only hands the accumulators back
+static int g_wgrad_flags = 0;
+extern "C" void efgh_debug_set_wgrad_flags(int flags) { g_wgrad_flags = flags; }
 
 namespace efgh {
 namespace {
 
 constexpr int kWM = 128;                       // conv-k rows per tile (MMA M)
 constexpr int kWStageV = 32;                   // vertices per stage (4 MMA K-steps)
-constexpr int kWMaxStages = 4;                 // ring of stages (as many as shared memory allows: 2 at N = 128, 3 at 64, 4 at 32)
-constexpr int kWTeams = 2;                     // producer teams of 4 warps; team t fills stages t, t+2, ... - two stages are always being gathered
+constexpr int kWMaxStages = 6;                 // ring of stages (as many as shared memory allows: 3 at N = 128, 4 at 64, 5 at 32)
+#ifndef EFGH_WGRAD_TEAMS
+#define EFGH_WGRAD_TEAMS 3
+#endif
+constexpr int kWTeams = EFGH_WGRAD_TEAMS;      // producer teams of 4 warps; team t fills stages t, t + kWTeams, ...: that many stages are being gathered at a time
 constexpr int kWCutStages = 8;                 // stages per accumulation chain (256 vertices)
-constexpr int kWProducerWarps = 8;
+constexpr int kWProducerWarps = 4 * kWTeams;
 constexpr int kWMmaWarp = kWProducerWarps, kWEpiWarp0 = kWProducerWarps + 1;
 constexpr int kWThreads = (kWEpiWarp0 + 4) * 32;   // 416
 
@@ -40,7 +51,7 @@ __device__ __forceinline__ void w_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void w_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 32) {
   uint32_t done = 0;
   while (true) {
     asm volatile(
@@ -55,6 +66,20 @@ __device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     __nanosleep(32);
   }
+}
+// non-blocking phase test (same for every lane of a converged warp only if the caller makes it so: see w_slot_free)
+__device__ __forceinline__ bool w_mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void w_commit(uint32_t bar) {
   asm volatile(
@@ -102,14 +127,32 @@ __device__ __forceinline__ void w_tmem_ld32(uint32_t taddr, float *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void w_tmem_st32(uint32_t taddr, const float *v) {
+  const uint32_t *r = reinterpret_cast<const uint32_t *>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 struct WgradParams {
   const float *X; int64_t ldX; int C;
   const void *nbr; int64_t nbr_ld; int F;
   int h_host; const int32_t *h_dev;
   const float *G; int64_t ldG; int M;
   float *dWt;                                 // (F*C, M) row-major, accumulated into
+  float *dbias;                               // optional (M): column sums of G, accumulated into (by the producers of the kt == 0 items)
   int K, n_kt, n_np, Np;                      // K = F*C; conv-k tiles; output-channel slices of Np columns
   int ring;                                   // stages in the shared-memory ring
+  int acc_stages;                             // accumulator stages in tensor memory (each 2 Np columns: main | correction)
+  int dbg;
+  int tmem_sum;                               // 1: the running sum of an item's chain cuts lives in tensor memory (columns 2 Np ..), not in shared memory
   uint32_t magic_c;
 };
 
@@ -139,13 +182,17 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
   const uint32_t stage_bytes = 2u * a_bytes + 2u * g_bytes;   // [A raw | A small | G raw | G small]
   const uint32_t ring = (uint32_t)p.ring;
   const uint32_t sum_base = smem_base + ring * stage_bytes;
-  const int pitch = Np + 4;                                    // floats per row of the running-sum tile
+  const int pitch = p.tmem_sum ? 36 : Np + 4;                  // floats per row of the running-sum tile / of the 32-column staging block
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)ring * stage_bytes + (size_t)kWM * pitch * 4);
-  // barriers: full[4] empty[4] acc_full[2] acc_empty[2]
-  const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 32, bar_acc_full = bar_full + 64, bar_acc_empty = bar_full + 80;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 12);
+  // barriers: full[8] empty[8] acc_full[2] acc_empty[2]
+  const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 64, bar_acc_full = bar_full + 128, bar_acc_empty = bar_full + 144;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // poll intervals of the three roles (timing studies override them: flags bits 8-15 / 16-23 / 24-31, units of 8 ns)
+  const uint32_t ns_prod = ((uint32_t)p.dbg >> 8 & 0xffu) ? ((uint32_t)p.dbg >> 8 & 0xffu) * 8u : 32u;
+  const uint32_t ns_epi = ((uint32_t)p.dbg >> 16 & 0xffu) ? ((uint32_t)p.dbg >> 16 & 0xffu) * 8u : 32u;
+  const uint32_t ns_mma = ((uint32_t)p.dbg >> 24 & 0xffu) ? ((uint32_t)p.dbg >> 24 & 0xffu) * 8u : 32u;
   const int H = p.h_dev ? min(*p.h_dev, p.h_host) : p.h_host;
   const int n_stages = (H + kWStageV - 1) / kWStageV;
   const int per = p.n_kt * p.n_np;
@@ -159,7 +206,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(s_tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(w_smem_u32(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -221,18 +268,44 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
     const int64_t xoff = p.nbr ? 0 : -(int64_t)p.ldX;          // without a neighbour table X has no sink row: row h+1 -> h
     bool pending = false;
     uint32_t pend_slot = 0;
+    // dbias (column sums of G): the producers of the kt == 0 items see every G row of their output slice exactly once
+    // (each (vertex range, output slice) pair has one kt == 0 item; rows beyond H are zero-filled), so they add what they
+    // convert anyway: lane = 4 columns x the 8 rows it copied.  Flushed when the output slice changes and at the end.
+    const bool want_bias = p.dbias != nullptr && has_g;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    int csum_np = -1, pend_np = -1;                           // pend_np >= 0: the pending stage belongs to a kt == 0 item
+    auto flush_csum = [&]() {
+      if (csum_np >= 0) {
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+          csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+          csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+        }
+        if (vsub == 0) {
+          float *db = p.dbias + csum_np * Np + 32 * g + 4 * u;
+          if (csum.x != 0.f) atomicAdd(db, csum.x);
+          if (csum.y != 0.f) atomicAdd(db + 1, csum.y);
+          if (csum.z != 0.f) atomicAdd(db + 2, csum.z);
+          if (csum.w != 0.f) atomicAdd(db + 3, csum.w);
+        }
+      }
+      csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     // landed stage -> "small" tiles -> publish.  keep_newest: the copy group committed last belongs to the NEXT stage
     auto complete_pending = [&](bool keep_newest) {
       if (keep_newest) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
       const uint32_t sbase = smem_base + pend_slot * stage_bytes;
+      const bool sum_g = want_bias && pend_np >= 0;           // (warp-uniform)
+      if (sum_g && pend_np != csum_np) { flush_csum(); csum_np = pend_np; }
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        if (part == 1 && !has_g) break;
+        if ((part == 1 && !has_g) || (p.dbg & 2)) break;
         const uint32_t raw = sbase + (part ? 2u * a_bytes : 0u), small = raw + (part ? g_bytes : a_bytes);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 x;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(raw + doff[i]));
+          if (part == 1 && sum_g) { csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w; }
           float4 sm;
           sm.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
           sm.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
@@ -246,22 +319,25 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
       if (lane == 0) w_mbar_arrive(bar_full + 8 * pend_slot);
       pending = false;
     };
-    // A team's consecutive stages are kWTeams apart in the ring.  With a ring that short (N = 128: two stages) the slot of
-    // the stage to issue is the one still pending, so the pending stage must be published BEFORE waiting for the slot -
-    // otherwise the team would wait for an MMA that waits for the team.
+    // A team's consecutive stages are kWTeams apart in the ring.  Issuing the next stage's copies BEFORE converting the
+    // pending one hides the copy latency - but only if the next stage's slot is free.  When it is not (always with a ring
+    // of two: the slot is the pending one), waiting for it with the pending stage unpublished stalls the MMA issuer that
+    // has to free it: measured, every stage then cost one full MMA + wake-up + issue + convert round trip (1.2 - 1.5 us
+    // whatever its size).  So: slot free -> issue first, convert while the copies fly; slot busy -> publish first.
     const bool serial = ring <= (uint32_t)kWTeams;
     while (pos_valid(pi) || pending) {
       const bool issue = pos_valid(pi);
-      if (pending && (serial || !issue)) complete_pending(false);
+      const uint32_t slot = pi.count % ring, slot_par = ((pi.count / ring) & 1u) ^ 1u;
+      if (pending && (serial || !issue || !__all_sync(0xffffffffu, w_mbar_test(bar_empty + 8 * slot, slot_par)))) complete_pending(false);
       if (issue) {
-        const uint32_t slot = pi.count % ring;
-        w_mbar_wait(bar_empty + 8 * slot, ((pi.count / ring) & 1u) ^ 1u);    // the MMAs that read this slot have retired
+        w_mbar_wait(bar_empty + 8 * slot, slot_par, ns_prod);                       // the MMAs that read this slot have retired
         const uint32_t sbase = smem_base + slot * stage_bytes;
         const int h0 = pi.st * kWStageV + vsub;
         const int k = pi.it.kt * kWM + 32 * g + 4 * u;
         const int f = (int)__umulhi((uint32_t)k, p.magic_c);
         const float *xc = p.X + xoff + (k - f * p.C);
-        const bool k_ok = k < p.K;
+        const bool k_ok = k < p.K && !(p.dbg & 4);
+        if (!(p.dbg & 32))
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = rows_next[i] + 1;                       // matrix row; 0 = absent neighbour (zero-filled)
@@ -270,51 +346,60 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
                        "r"(nbytes)
                        : "memory");
         }
-        if (has_g) {
+        if (has_g && !(p.dbg & 32)) {
           const float *gc = p.G + pi.it.np * Np + 32 * g + 4 * u;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int h = h0 + 4 * i;
-            const uint32_t nbytes = h < H ? 16u : 0u;
+            const uint32_t nbytes = (h < H && !(p.dbg & 4)) ? 16u : 0u;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + 2u * a_bytes + doff[i]), "l"(gc + (int64_t)min(h, H - 1) * p.ldG),
                          "r"(nbytes)
                          : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        const int issued_np = pi.it.kt == 0 ? pi.it.np : -1;
         // this team's next stage: prefetch its row indices while the copies fly
         for (int k = 0; k < kWTeams && pos_valid(pi); ++k) pos_step(pi);
-        if (pos_valid(pi)) fetch_rows(pi, rows_next);
+        if (pos_valid(pi) && !(p.dbg & 64)) fetch_rows(pi, rows_next);
         if (pending) complete_pending(true);
         pending = true;
         pend_slot = slot;
+        pend_np = issued_np;
       }
     }
+    if (want_bias) flush_csum();
   } else if (warp == kWMmaWarp) {
     // ===================== MMA issuer =====================
     const uint32_t tmem = __shfl_sync(0xffffffffu, *s_tmem, 0);
-    const uint32_t idesc = w_idesc(Np);
+    const uint32_t idesc = w_idesc(Np), idesc2 = w_idesc(2 * Np);
     uint32_t count = 0, cuts = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const WItem it = w_item(p, item, n_stages, vsplit);
       for (int st = it.st_begin; st < it.st_end;) {
-        const uint32_t as = cuts & 1u, aph = (cuts >> 1) & 1u;
-        w_mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
+        const uint32_t as = p.acc_stages == 2 ? (cuts & 1u) : 0u, aph = p.acc_stages == 2 ? ((cuts >> 1) & 1u) : (cuts & 1u);
+        w_mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u, ns_mma);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem + as * (uint32_t)Np;
+        // 3xTF32 = A_raw G_raw + A_raw G_small + A_small G_raw.  The G tile holds [raw groups | small groups] back to back at
+        // the same group stride, so A_raw x [G_raw | G_small] is ONE MMA with N' = 2 Np into two adjacent accumulators
+        // (main | correction); A_small x G_raw joins the correction accumulator.  8 MMAs per stage instead of 12: with
+        // MN-major operands an MMA costs ~80-100 ns whatever its N (measured: 12 MMAs per stage took 1.18 / 0.93 / 0.75 us
+        // at N = 32 / 64 / 128), so the weight gradient is bound by the NUMBER of MMAs.  The epilogue adds the two
+        // accumulators with round-to-nearest adds.
+        const uint32_t d = tmem + as * (uint32_t)(2 * Np), d_corr = d + (uint32_t)Np;
         const int cut_end = min(it.st_end, st + kWCutStages);
         for (bool first = true; st < cut_end; ++st, ++count) {
           const uint32_t slot = count % ring;
-          w_mbar_wait(bar_full + 8 * slot, (count / ring) & 1u);
+          w_mbar_wait(bar_full + 8 * slot, (count / ring) & 1u, ns_mma);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = smem_base + slot * stage_bytes;
-          const uint32_t a_raw = sbase, a_small = sbase + a_bytes, g_raw = sbase + 2u * a_bytes, g_small = g_raw + g_bytes;
+          const uint32_t a_raw = sbase, a_small = sbase + a_bytes, g_raw = sbase + 2u * a_bytes;
 #pragma unroll
           for (int ks = 0; ks < kWStageV / 8; ++ks) {
+            if (((p.dbg & 1) && ks) || (p.dbg & 16)) break;
             const uint32_t o = (uint32_t)ks * 1024u;
-            w_umma_ss(d, w_desc(a_small + o, 4096u), w_desc(g_raw + o, 4096u), idesc, !(first && ks == 0));
-            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_small + o, 4096u), idesc, 1);
-            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_raw + o, 4096u), idesc, 1);
+            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_raw + o, 4096u), idesc2, !(first && ks == 0));
+            w_umma_ss(d_corr, w_desc(a_small + o, 4096u), w_desc(g_raw + o, 4096u), idesc, 1);
           }
           w_commit(bar_empty + 8 * slot);
           first = false;
@@ -333,15 +418,35 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
       const WItem it = w_item(p, item, n_stages, vsplit);
       const int n_cut = (it.st_end - it.st_begin + kWCutStages - 1) / kWCutStages;
       for (int c = 0; c < n_cut; ++c, ++cuts) {
-        const uint32_t as = cuts & 1u, aph = (cuts >> 1) & 1u;
+        const uint32_t as = p.acc_stages == 2 ? (cuts & 1u) : 0u, aph = p.acc_stages == 2 ? ((cuts >> 1) & 1u) : (cuts & 1u);
         const bool last = c == n_cut - 1;
-        w_mbar_wait(bar_acc_full + 8 * as, aph);
+        w_mbar_wait(bar_acc_full + 8 * as, aph, ns_epi);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int cb = 0; cb < Np; cb += 32) {
+          if (p.dbg & 8) break;
           float vv[32];
-          w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)Np + cb, vv);
-          const uint32_t my_row = tile + (uint32_t)lane * pitch_b + (uint32_t)cb * 4u;
-          if (c > 0) {
+          {
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)(2 * Np) + cb;
+            float cc[32];
+            w_tmem_ld32(acc, vv);
+            w_tmem_ld32(acc + (uint32_t)Np, cc);                  // correction products (round-to-nearest add)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vv[i] += cc[i];
+          }
+          const uint32_t col_b = p.tmem_sum ? 0u : (uint32_t)cb * 4u;           // (tensor-memory sums: one 32-column staging block)
+          const uint32_t my_row = tile + (uint32_t)lane * pitch_b + col_b;
+          if (p.tmem_sum) {
+            // running sum in tensor memory: each thread adds into its own lane's columns - no shared memory until the
+            // last cut, whose 32-column block goes through the small staging tile for the transposed reductions
+            const uint32_t racc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.acc_stages * 2 * Np) + (uint32_t)cb;
+            if (c > 0) {
+              float rr[32];
+              w_tmem_ld32(racc, rr);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vv[i] += rr[i];
+            }
+            if (!last) { w_tmem_st32(racc, vv); continue; }
+          } else if (c > 0) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               float4 r;
@@ -364,7 +469,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
             float4 o;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                         : "r"(tile + (uint32_t)row * pitch_b + (uint32_t)cb * 4u + (uint32_t)(lane & 7) * 16u));
+                         : "r"(tile + (uint32_t)row * pitch_b + col_b + (uint32_t)(lane & 7) * 16u));
             const int k = k_warp + row;
             if (k < p.K) atomicAdd(reinterpret_cast<float4 *>(p.dWt + (int64_t)k * p.M + it.np * Np + cb + 4 * (lane & 7)), o);
           }
@@ -379,36 +484,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kWMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
-}
-
-// dbias[m] += sum_h G[h, m]: thread = (float4 column group, row lane), rows strided over the grid; one atomic per column
-// and CTA.  HBM-bound: G is read once with 16-byte loads.
-__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ G, int64_t ldG, int M, int h_host, const int32_t *h_dev, float *dbias) {
-  __shared__ float4 s_part[256];
-  const int H = h_dev ? min(*h_dev, h_host) : h_host;
-  const int M4 = M >> 2;                                       // <= 64
-  const int lanes = 256 / M4;                                  // row lanes per CTA
-  const int cg = threadIdx.x % M4, rl = threadIdx.x / M4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rl < lanes) {
-    for (int h = blockIdx.x * lanes + rl; h < H; h += gridDim.x * lanes) {
-      const float4 x = __ldg(reinterpret_cast<const float4 *>(G + (int64_t)h * ldG) + cg);
-      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-    }
-  }
-  s_part[threadIdx.x] = acc;
-  __syncthreads();
-  if (rl == 0) {
-    for (int r = 1; r < lanes; ++r) {
-      const float4 q = s_part[r * M4 + cg];
-      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-    }
-    if (acc.x != 0.f) atomicAdd(dbias + 4 * cg, acc.x);
-    if (acc.y != 0.f) atomicAdd(dbias + 4 * cg + 1, acc.y);
-    if (acc.z != 0.f) atomicAdd(dbias + 4 * cg + 2, acc.z);
-    if (acc.w != 0.f) atomicAdd(dbias + 4 * cg + 3, acc.w);
-  }
+  if (warp == kWMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -416,9 +492,9 @@ __global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ G, int
 
 using namespace efgh;
 
-static size_t wgrad_tc_smem(int Np, int *ring_out) {
+static size_t wgrad_tc_smem(int Np, bool tmem_sum, int *ring_out) {
   const size_t stage = 2 * 4 * 4096 + 2 * (size_t)(Np / 32) * 4096;
-  const size_t fixed = (size_t)kWM * (Np + 4) * 4 + 128 + 1024;
+  const size_t fixed = (size_t)kWM * (tmem_sum ? 36 : Np + 4) * 4 + 256 + 1024;
   int ring = (int)((226 * 1024 - fixed) / stage);
   if (ring > kWMaxStages) ring = kWMaxStages;
   if (ring_out) *ring_out = ring;
@@ -445,12 +521,19 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
   EFGH_REQUIRE(idx_bits == 32 || idx_bits == 64, "efgh_bcl_conv_wgrad_tc: idx_bits must be 32 or 64");
   WgradParams p;
   p.X = X; p.ldX = ldX; p.C = C; p.nbr = nbr; p.nbr_ld = nbr_ld; p.F = F; p.h_host = (int)h; p.h_dev = h_dev;
-  p.G = dY; p.ldG = ldY; p.M = M; p.dWt = dWt; p.K = F * C;
+  p.G = dY; p.ldG = ldY; p.M = M; p.dWt = dWt; p.dbias = dbias; p.K = F * C;
   p.n_kt = (p.K + kWM - 1) / kWM;
   p.Np = M > 128 ? 128 : M;
   p.n_np = M / p.Np;
   p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
-  const size_t smem = wgrad_tc_smem(p.Np, &p.ring);
+  // running sum of the chain cuts in tensor memory (3 Np <= 512 columns): frees 128 x Np x 4 bytes of shared memory for
+  // a deeper stage ring (N = 128: three stages instead of two).  EFGH_WGRAD_SMEM_SUM=1 keeps the shared-memory tile.
+  static const bool smem_sum = getenv("EFGH_WGRAD_SMEM_SUM") && atoi(getenv("EFGH_WGRAD_SMEM_SUM")) != 0;
+  p.tmem_sum = smem_sum ? 0 : 1;
+  p.dbg = g_wgrad_flags;
+  // tensor memory (512 columns): acc_stages x (main | correction) x Np + the running sum (Np)
+  p.acc_stages = (2 * 2 * p.Np + (p.tmem_sum ? p.Np : 0)) <= 512 ? 2 : 1;
+  const size_t smem = wgrad_tc_smem(p.Np, p.tmem_sum != 0, &p.ring);
   EFGH_REQUIRE(p.ring >= 2, "efgh_bcl_conv_wgrad_tc: no room for two stages");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = sm_count();
@@ -464,9 +547,5 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
     kern<<<grid, kWThreads, smem, s>>>(p);
   }
   EFGH_LAUNCH_CHECK();
-  if (dbias) {
-    k_colsum<<<grid_for(h * (M / 4), 256 * 4, 8), 256, 0, s>>>(dY, ldY, M, (int)h, h_dev, dbias);
-    EFGH_LAUNCH_CHECK();
-  }
   return EFGH_OK;
 }

@@ -25,6 +25,9 @@ KEYS = {
     "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio": "stall_sleeping",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",
     "sm__inst_executed.sum": "warp_instructions",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed": "l1tex_pct_of_peak",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct_of_peak",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct_of_peak",
 }
 
 

@@ -172,6 +172,50 @@ __device__ __forceinline__ void umma_chunk_3x(uint32_t d_main, uint32_t d_sb, ui
       "}" ::"r"(d_main), "r"(d_sb), "r"(a_big), "l"(desc_b), "r"(idesc2), "r"(idesc), "r"(acc_main), "r"(acc_sb), "r"(bar_a), "r"(bar_b)
       : "memory");
 }
+// The same for ONE accumulator (N >= 128: no tensor-memory columns to spare for correction accumulators): 4 k-steps x
+// [A_small x B_big, A_big x B_small, A_big x B_big] -> d, then the two commits, under one election with the operand
+// increments done once.  tools/umma_chain_probe.cu: an MMA issued from a block like this costs 15 / 18 / 36 / 71 ns at
+// N = 32 / 64 / 128 / 256 (the math floor), ~100 ns of the issuing warp's time from a per-MMA loop.  Measured effect here:
+// level-2 conv1 (N = 128) 455 -> 445 us per 16 scans - the issuer was not the bound, the block is simply the cheaper form.
+__device__ __forceinline__ void umma_chunk_3x_1acc(uint32_t d, uint32_t a_big, uint64_t desc_bb, uint64_t desc_bs, uint32_t idesc,
+                                                    uint32_t acc_first, uint32_t bar_a, uint32_t bar_b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf;\n\t"
+      ".reg .b32 a1, a2, a3, s0, s1, s2, s3;\n\t"
+      ".reg .b64 b1, b2, b3, c1, c2, c3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %5, 0;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 a2, %1, 16;\n\t"
+      "add.u32 a3, %1, 24;\n\t"
+      "add.u32 s0, %1, 32;\n\t"
+      "add.u32 s1, %1, 40;\n\t"
+      "add.u32 s2, %1, 48;\n\t"
+      "add.u32 s3, %1, 56;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "add.u64 c1, %3, 2;\n\t"
+      "add.u64 c2, %3, 4;\n\t"
+      "add.u64 c3, %3, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [s0], %2, %4, pf;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [s1], b1, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], c1, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a1], b1, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [s2], b2, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], c2, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a2], b2, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [s3], b3, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], c3, %4, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [a3], b3, %4, 1;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "}" ::"r"(d), "r"(a_big), "l"(desc_bb), "l"(desc_bs), "r"(idesc), "r"(acc_first), "r"(bar_a), "r"(bar_b)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -602,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
           mbar_wait(bar_b_full + 8 * sb, phb);
           tc_fence_after();
           if (lane == 0) trace_ev(p.trace, 3, ntrace, 2);
-          const uint32_t a_big = tmem_base + a_ring_col + team * kAStageCols, a_small = a_big + 32;
+          const uint32_t a_big = tmem_base + a_ring_col + team * kAStageCols;      // (the remainder half follows at + 32 columns)
           const uint32_t b_big = smem_base + sb * b_bytes, b_small = b_big + (uint32_t)N * 128u;
           const uint64_t dbb = make_desc(b_big);
           const uint32_t first = j == j_begin;
@@ -610,18 +654,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const ConvParams p) {
             umma_chunk_3x(tmem_d0, d_sb, a_big, dbb, idesc2, idesc, !first, !(first && p.nacc == 3), bar_a_empty + 8 * team,
                           bar_b_empty + 8 * sb);
           } else if (NSPLIT == 3) {
-            const uint64_t dbs = make_desc(b_small);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts(tmem_d0, a_small + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
-              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbs + 2 * k4, idesc, 1);
-              umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc, 1);
-            }
+            umma_chunk_3x_1acc(tmem_d0, a_big, dbb, make_desc(b_small), idesc, !first, bar_a_empty + 8 * team, bar_b_empty + 8 * sb);
           } else {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) umma_tf32_ts(tmem_d0, a_big + 8 * k4, dbb + 2 * k4, idesc, !(first && k4 == 0));
           }
-          if (!(NSPLIT == 3 && p.nacc >= 2)) {
+          if (NSPLIT != 3) {
             umma_commit(bar_a_empty + 8 * team);             // frees the team's TMEM A stage when these MMAs retire
             umma_commit(bar_b_empty + 8 * sb);               // ... and the weight stage
           }

@@ -26,7 +26,7 @@
 #include "common.cuh"
 
 // Timing-study switches (tools/wgrad_tc_time.py; results are WRONG with any of them set):
-//   bit 0  the MMA issuer issues only the first MMA pair of a stage      bit 1  producers skip the "small" tiles
+//   bit 0  the MMA issuer issues only the first k-step of a stage        bit 1  producers skip the "small" tiles
 //   bit 2  producers skip the copies                                     bit 3  the epilogue only hands the accumulators back
 static int g_wgrad_flags = 0;
 extern "C" void efgh_debug_set_wgrad_flags(int flags) { g_wgrad_flags = flags; }
@@ -99,6 +99,47 @@ __device__ __forceinline__ void w_umma_ss(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// One stage (32 vertices = 4 k-steps of 1024 bytes) under ONE election, descriptors advanced inside the block:
+//   A_raw x [G_raw | G_small] -> d (N' = 2 Np: main | correction),  A_small x G_raw -> d_corr (N = Np),
+// then the commit that frees the stage.  tools/umma_chain_probe.cu: an MMA issued from a block like this costs 15 / 18 / 36 /
+// 71 ns at N = 32 / 64 / 128 / 256, ~100 ns of the issuing warp's time from a per-MMA loop (election, predicate, descriptor
+// arithmetic each time).  Measured effect here: 1 204 -> 1 187 us over the ten launches of a training step - the kernel is
+// bound by its producer teams, the block is simply the cheaper form.
+__device__ __forceinline__ void w_umma_stage_ss(uint32_t d, uint32_t d_corr, uint64_t desc_a_raw, uint64_t desc_a_small, uint64_t desc_g_raw,
+                                                 uint32_t idesc2, uint32_t idesc, uint32_t acc_first, uint32_t bar_empty, int ksteps) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, pf, p1, p2, p3;\n\t"
+      ".reg .b64 a1, a2, a3, s1, s2, s3, g1, g2, g3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"
+      "setp.gt.s32 p1, %9, 1;\n\t"
+      "setp.gt.s32 p2, %9, 2;\n\t"
+      "setp.gt.s32 p3, %9, 3;\n\t"
+      "and.pred p1, p1, e;\n\t"
+      "and.pred p2, p2, e;\n\t"
+      "and.pred p3, p3, e;\n\t"
+      "add.u64 a1, %2, 64;\n\t"
+      "add.u64 a2, %2, 128;\n\t"
+      "add.u64 a3, %2, 192;\n\t"
+      "add.u64 s1, %3, 64;\n\t"
+      "add.u64 s2, %3, 128;\n\t"
+      "add.u64 s3, %3, 192;\n\t"
+      "add.u64 g1, %4, 64;\n\t"
+      "add.u64 g2, %4, 128;\n\t"
+      "add.u64 g3, %4, 192;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %5, pf;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, 1;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, g1, %5, 1;\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::tf32 [%1], s1, g1, %6, 1;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, g2, %5, 1;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::tf32 [%1], s2, g2, %6, 1;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, g3, %5, 1;\n\t"
+      "@p3 tcgen05.mma.cta_group::1.kind::tf32 [%1], s3, g3, %6, 1;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "}" ::"r"(d), "r"(d_corr), "l"(desc_a_raw), "l"(desc_a_small), "l"(desc_g_raw), "r"(idesc2), "r"(idesc), "r"(acc_first), "r"(bar_empty), "r"(ksteps)
       : "memory");
 }
 // MN-major, SWIZZLE_128B_BASE32B (layout type 1), descriptor version 1: LBO = stride between 32-element MN groups,
@@ -382,10 +423,8 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // 3xTF32 = A_raw G_raw + A_raw G_small + A_small G_raw.  The G tile holds [raw groups | small groups] back to back at
         // the same group stride, so A_raw x [G_raw | G_small] is ONE MMA with N' = 2 Np into two adjacent accumulators
-        // (main | correction); A_small x G_raw joins the correction accumulator.  8 MMAs per stage instead of 12: with
-        // MN-major operands an MMA costs ~80-100 ns whatever its N (measured: 12 MMAs per stage took 1.18 / 0.93 / 0.75 us
-        // at N = 32 / 64 / 128), so the weight gradient is bound by the NUMBER of MMAs.  The epilogue adds the two
-        // accumulators with round-to-nearest adds.
+        // (main | correction); A_small x G_raw joins the correction accumulator: 8 MMAs per stage instead of 12, issued as
+        // one block (w_umma_stage_ss).  The epilogue adds the two accumulators with round-to-nearest adds.
         const uint32_t d = tmem + as * (uint32_t)(2 * Np), d_corr = d + (uint32_t)Np;
         const int cut_end = min(it.st_end, st + kWCutStages);
         for (bool first = true; st < cut_end; ++st, ++count) {
@@ -394,14 +433,8 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sbase = smem_base + slot * stage_bytes;
           const uint32_t a_raw = sbase, a_small = sbase + a_bytes, g_raw = sbase + 2u * a_bytes;
-#pragma unroll
-          for (int ks = 0; ks < kWStageV / 8; ++ks) {
-            if (((p.dbg & 1) && ks) || (p.dbg & 16)) break;
-            const uint32_t o = (uint32_t)ks * 1024u;
-            w_umma_ss(d, w_desc(a_raw + o, 4096u), w_desc(g_raw + o, 4096u), idesc2, !(first && ks == 0));
-            w_umma_ss(d_corr, w_desc(a_small + o, 4096u), w_desc(g_raw + o, 4096u), idesc, 1);
-          }
-          w_commit(bar_empty + 8 * slot);
+          w_umma_stage_ss(d, d_corr, w_desc(a_raw, 4096u), w_desc(a_small, 4096u), w_desc(g_raw, 4096u), idesc2, idesc, !first, bar_empty + 8 * slot,
+                          (p.dbg & 1) ? 1 : kWStageV / 8);
           first = false;
         }
         w_commit(bar_acc_full + 8 * as);

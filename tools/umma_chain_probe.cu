@@ -18,7 +18,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {      // K-major, 
 }
 
 // n_acc accumulators of N columns each; MMA i goes to accumulator i % n_acc.  a_tmem: A operand from tensor memory.
-__global__ void __launch_bounds__(128) k_chain(int N, int n_acc, int n_mma, int a_tmem, unsigned long long *ns_out) {
+__global__ void __launch_bounds__(128) k_chain(int N, int n_acc, int n_mma, int a_tmem, unsigned long long *ns_out, int b_mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
@@ -40,8 +40,11 @@ __global__ void __launch_bounds__(128) k_chain(int N, int n_acc, int n_mma, int 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = s_tmem;
   const uint32_t a_col = 448;                                        // A stage (64 columns) behind the accumulators
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint64_t db = make_desc(base), da = make_desc(base + 256 * 128);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // b_mn: B MN-major as k_wgrad_tc has it (SWIZZLE_128B_BASE32B, 32-column groups 4096 B apart, 4-row K atoms 512 B apart);
+  // the k-step advance inside the blocks below (+2 x 16 B) is not the real one (+1024 B) - timing only, the data are arbitrary
+  const uint64_t db = b_mn ? ((uint64_t)((512u >> 4) | (1u << 14) | (1u << 29)) << 32) | (((base & 0x3ffff) >> 4) | ((4096u >> 4) << 16)) : make_desc(base);
+  const uint64_t da = make_desc(base + 256 * 128);
   unsigned long long t0 = 0, t1 = 0;
   // the WHOLE warp 0 runs the loop converged and one elected lane issues (as the kernels do: under `if (tid == 0)` ptxas
   // wraps every MMA in a value-uniformising loop)
@@ -110,15 +113,16 @@ int main() {
   const int smem = (256 + 128) * 128 + 1024;
   CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_mma = 4096;
+  for (int b_mn = 0; b_mn <= 1; ++b_mn)
   for (int a_tmem = 1; a_tmem >= 0; --a_tmem)
     for (int N = 32; N <= 256; N *= 2)
-      for (int n_acc = 1; n_acc * N <= 384 && n_acc <= 8; n_acc *= 2) {
+      for (int n_acc = 1; n_acc * N <= 384 && n_acc <= 2; n_acc *= 2) {
         for (int rep = 0; rep < 2; ++rep) {
-          k_chain<<<148, 128, smem>>>(N, n_acc, n_mma, a_tmem, dns);
+          k_chain<<<148, 128, smem>>>(N, n_acc, n_mma, a_tmem, dns, b_mn);
           CK(cudaDeviceSynchronize());
         }
         CK(cudaMemcpy(hns, dns, 16, cudaMemcpyDeviceToHost));
-        printf("A %s, N = %3d, %d accumulator(s): issue %.1f ns per MMA, retire %.1f ns per MMA  (math floor %.1f ns at 1.9 GHz)\n", a_tmem ? "tmem" : "smem", N, n_acc,
+        printf("B %s, A %s, N = %3d, %d accumulator(s): issue %.1f ns per MMA, retire %.1f ns per MMA  (math floor %.1f ns at 1.9 GHz)\n", b_mn ? "MN-major" : "K-major", a_tmem ? "tmem" : "smem", N, n_acc,
                (double)hns[0] / n_mma, (double)hns[1] / n_mma, 128.0 * N / 256.0 / 1.9);
       }
   return 0;

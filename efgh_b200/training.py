@@ -40,7 +40,7 @@ class ModulePathTrainer(object):
         torch.manual_seed(seed)                               # identical replicas
         self.dev, self.world = dev, world
         self.model = Enet(dict(ENET_ARGS)).to(dev)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)    # one multi-tensor kernel instead of ~60 small ones
         self.clouds = [c[None] for c in clouds]
         self.allreduce_calls = 0
 
@@ -81,7 +81,7 @@ class BatchedTrainer(object):
             self.stem = model.conv_in
             self.bcns = nn.ModuleList([model.bcn1, model.bcn2, model.bcn3, model.bcn4, model.bcn5])
             self.params = list(self.stem.parameters()) + list(self.bcns.parameters())
-            self.opt = torch.optim.Adam(self.params, lr=lr)
+            self.opt = torch.optim.Adam(self.params, lr=lr, fused=True)           # one multi-tensor kernel instead of ~60 small ones
             plan = [(m.num_input, list(m.num_output)) for m in self.bcns]
             self.pipe = ScanPipeline(n, synth.SCALE_MAP, plan, self._weights(), dev, vertex_cap_factor=vertex_cap_factor,
                                      emit_int64=False, batch=B, precision=precision, train=True)
@@ -144,7 +144,9 @@ class BatchedTrainer(object):
             for m, g in zip(self.bcns, pipe.weight_grads()):
                 convs = [c for c in m.blur_conv if isinstance(c, nn.Conv2d)]
                 for c, (gw, gb) in zip(convs, g):
-                    c.weight.grad, c.bias.grad = gw, gb
+                    # (the pipeline's gradients are permuted VIEWS of its (K, M) buffers; the optimizer's multi-tensor kernels
+                    #  need the parameter's own layout - with strided gradients torch falls back to ~60 per-tensor kernels)
+                    c.weight.grad, c.bias.grad = gw.contiguous(), gb
             self.allreduce_calls = sharding.allreduce_gradients(self.params, self.world)
             self.opt.step()
         return self._loss_dev

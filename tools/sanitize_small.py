@@ -40,3 +40,26 @@ try:
 except VertexCapExceeded as e:
     print("overflow reported:", e)
 torch.cuda.synchronize()
+
+# ---- round-2 kernels: warp-private splat with the fused stem, batched backward (tensor-core weight gradient, k_act_bwd,
+#      loss), image projections and pre-processing
+gs_ = torch.Generator().manual_seed(5)
+stem_layers = [(torch.randn(co, ci, 1, generator=gs_) * 0.3, torch.randn(co, generator=gs_) * 0.1) for ci, co in ((3, 32), (32, 32), (32, 32))]
+pstem = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=16.0, batch=2, stem=(stem_layers, True))
+pstem.enqueue(torch.from_numpy(np.concatenate(clouds, 1)).to(dev), None)
+print("stem-fused counts", pstem.counts())
+ptrain = ScanPipeline(n, synth.SCALE_MAP, synth.ENET_BCL, weights, dev, vertex_cap_factor=16.0, emit_int64=False, batch=2, train=True)
+ptrain.enqueue(torch.from_numpy(np.concatenate(clouds, 1)).to(dev), feats.to(dev))
+loss, dZ = ptrain.loss_half_mean_square()
+dfeat = ptrain.backward(dZ)
+torch.cuda.synchronize()
+print("batched backward ok", float(loss), float(dfeat.abs().sum()), float(ptrain.weight_grads()[0][0][0].abs().sum()))
+from efgh_b200 import projections, preproc
+pc3 = torch.from_numpy(clouds[0])[None].to(dev)
+ri = projections.range_img_from_cartesian_pc_torch(pc3, (64, 256), (0.4, -0.4), "cuda")
+T = torch.eye(4)[:3][None].to(dev) * 100.0
+di = projections.depth_img_from_cartesian_pc_torch(pc3, T, (64, 128), "cuda")
+pcd = np.concatenate((clouds[0].T, np.ones((n, 1), np.float32)), 1)
+out = preproc.preproc_pcd(pcd, {"rand_init_l": np.eye(4)}, 1024, radius=50.0)
+torch.cuda.synchronize()
+print("projections / preproc ok", tuple(ri.shape), tuple(di.shape), tuple(out.shape))

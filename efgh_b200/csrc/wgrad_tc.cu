@@ -193,7 +193,6 @@ struct WgradParams {
   int ring;                                   // stages in the shared-memory ring
   int acc_stages;                             // accumulator stages in tensor memory (each 2 Np columns: main | correction)
   int dbg;
-  int tmem_sum;                               // 1: the running sum of an item's chain cuts lives in tensor memory (columns 2 Np ..), not in shared memory
   uint32_t magic_c;
 };
 
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
   const uint32_t stage_bytes = 2u * a_bytes + 2u * g_bytes;   // [A raw | A small | G raw | G small]
   const uint32_t ring = (uint32_t)p.ring;
   const uint32_t sum_base = smem_base + ring * stage_bytes;
-  const int pitch = p.tmem_sum ? 36 : Np + 4;                  // floats per row of the running-sum tile / of the 32-column staging block
+  const int pitch = 36;                                        // floats per row of the 32-column staging block of the epilogue
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)ring * stage_bytes + (size_t)kWM * pitch * 4);
   // barriers: full[8] empty[8] acc_full[2] acc_empty[2]
   const uint32_t bar_full = w_smem_u32(bars), bar_empty = bar_full + 64, bar_acc_full = bar_full + 128, bar_acc_empty = bar_full + 144;
@@ -466,11 +465,10 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
 #pragma unroll
             for (int i = 0; i < 32; ++i) vv[i] += cc[i];
           }
-          const uint32_t col_b = p.tmem_sum ? 0u : (uint32_t)cb * 4u;           // (tensor-memory sums: one 32-column staging block)
-          const uint32_t my_row = tile + (uint32_t)lane * pitch_b + col_b;
-          if (p.tmem_sum) {
-            // running sum in tensor memory: each thread adds into its own lane's columns - no shared memory until the
-            // last cut, whose 32-column block goes through the small staging tile for the transposed reductions
+          const uint32_t my_row = tile + (uint32_t)lane * pitch_b;
+          {
+            // running sum of the item's chain cuts in tensor memory: each thread adds into its own lane's columns - no shared
+            // memory until the last cut, whose 32-column block goes through the small staging tile for the transposed reductions
             const uint32_t racc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.acc_stages * 2 * Np) + (uint32_t)cb;
             if (c > 0) {
               float rr[32];
@@ -479,20 +477,12 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
               for (int i = 0; i < 32; ++i) vv[i] += rr[i];
             }
             if (!last) { w_tmem_st32(racc, vv); continue; }
-          } else if (c > 0) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              float4 r;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(my_row + (uint32_t)u * 16u));
-              vv[4 * u] += r.x; vv[4 * u + 1] += r.y; vv[4 * u + 2] += r.z; vv[4 * u + 3] += r.w;
-            }
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)u * 16u), "f"(vv[4 * u]), "f"(vv[4 * u + 1]),
                          "f"(vv[4 * u + 2]), "f"(vv[4 * u + 3])
                          : "memory");
-          if (!last) continue;
           __syncwarp();
           // transposed read-back: every reduction instruction covers 4 rows x 128 contiguous bytes of dWt
           const int k_warp = it.kt * kWM + q * 32;
@@ -502,7 +492,7 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
             float4 o;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                         : "r"(tile + (uint32_t)row * pitch_b + col_b + (uint32_t)(lane & 7) * 16u));
+                         : "r"(tile + (uint32_t)row * pitch_b + (uint32_t)(lane & 7) * 16u));
             const int k = k_warp + row;
             if (k < p.K) atomicAdd(reinterpret_cast<float4 *>(p.dWt + (int64_t)k * p.M + it.np * Np + cb + 4 * (lane & 7)), o);
           }
@@ -525,9 +515,9 @@ __global__ void __launch_bounds__(kWThreads, 1) k_wgrad_tc(const WgradParams p) 
 
 using namespace efgh;
 
-static size_t wgrad_tc_smem(int Np, bool tmem_sum, int *ring_out) {
+static size_t wgrad_tc_smem(int Np, int *ring_out) {
   const size_t stage = 2 * 4 * 4096 + 2 * (size_t)(Np / 32) * 4096;
-  const size_t fixed = (size_t)kWM * (tmem_sum ? 36 : Np + 4) * 4 + 256 + 1024;
+  const size_t fixed = (size_t)kWM * 36 * 4 + 256 + 1024;
   int ring = (int)((226 * 1024 - fixed) / stage);
   if (ring > kWMaxStages) ring = kWMaxStages;
   if (ring_out) *ring_out = ring;
@@ -559,14 +549,11 @@ extern "C" int efgh_bcl_conv_wgrad_tc(const float *X, int64_t ldX, int C, const 
   p.Np = M > 128 ? 128 : M;
   p.n_np = M / p.Np;
   p.magic_c = (uint32_t)(((1ull << 32) + (uint64_t)C - 1) / (uint64_t)C);
-  // running sum of the chain cuts in tensor memory (3 Np <= 512 columns): frees 128 x Np x 4 bytes of shared memory for
-  // a deeper stage ring (N = 128: three stages instead of two).  EFGH_WGRAD_SMEM_SUM=1 keeps the shared-memory tile.
-  static const bool smem_sum = getenv("EFGH_WGRAD_SMEM_SUM") && atoi(getenv("EFGH_WGRAD_SMEM_SUM")) != 0;
-  p.tmem_sum = smem_sum ? 0 : 1;
   p.dbg = g_wgrad_flags;
-  // tensor memory (512 columns): acc_stages x (main | correction) x Np + the running sum (Np)
-  p.acc_stages = (2 * 2 * p.Np + (p.tmem_sum ? p.Np : 0)) <= 512 ? 2 : 1;
-  const size_t smem = wgrad_tc_smem(p.Np, p.tmem_sum != 0, &p.ring);
+  // tensor memory (512 columns): acc_stages x (main | correction) x Np + the running sum of the chain cuts (Np) - keeping
+  // that sum in tensor memory instead of a 128 x Np shared-memory tile is what leaves room for a ring of 5 / 4 / 3 stages
+  p.acc_stages = (2 * 2 * p.Np + p.Np) <= 512 ? 2 : 1;
+  const size_t smem = wgrad_tc_smem(p.Np, &p.ring);
   EFGH_REQUIRE(p.ring >= 2, "efgh_bcl_conv_wgrad_tc: no room for two stages");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = sm_count();

@@ -304,3 +304,4 @@ def test_batched_trainer_matches_module_path_trainer(dev):
 def bt_gd(dev):
     from efgh_b200.generate_data import GenerateData
     return GenerateData(3, synth.SCALE_MAP, "cuda", exact=False)
+

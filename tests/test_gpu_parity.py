@@ -591,3 +591,20 @@ def test_bcl_partition_of_unity_fullsize(dev):
                 d["pc1_barycentric"], d["pc1_lattice_offset"])
     assert tuple(out.shape) == (1, C, pc.shape[1])
     assert float((out - 1).abs().max()) < 2e-4       # 1e-5 in the normaliser's denominator, fp32 sums
+
+
+@pytest.mark.gpu
+def test_scatter_kernel_variants_in_subprocess():
+    """The level-0 splat has two kernels (tile: CTA-wide tile + barriers; warp: warp-private tiles) of which the library
+    picks one per case (warp with the fused stem, tile otherwise); EFGH_SCATTER forces either for every case.  The
+    choice is latched at the first call, so each forced variant runs the oracle comparisons in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for variant in ("warp", "tile"):
+        env = dict(os.environ, EFGH_SCATTER=variant)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
+                            "-k", "test_scan_pipeline_vs_oracle or test_fused_stem_pipeline or test_batched_pipeline_matches_single_scans"],
+                           cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, "EFGH_SCATTER=%s:\n%s\n%s" % (variant, r.stdout[-3000:], r.stderr[-2000:])

@@ -92,7 +92,8 @@ def _oracle_grads(m, d, feat, gout, mask):
 def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch):
     """Every E-Net BCL shape (36->[32,32] ... 260->[256,256]) on its REAL lattice level of a 16k and a 65k cloud:
     forward within 1e-5 and d features / d weights / d biases within 2e-5 of the float64 oracle's autograd - for the
-    tensor-core (gather-form) and the scatter-form data gradient, with int64 and int32 lattice indices.  Both sides
+    tensor-core (gather-form) data gradient + tensor-core weight gradient and the scatter-form data gradient + fp32 CUDA-core
+    weight gradient, with int64 and int32 lattice indices.  Both sides
     differentiate the inner ReLU with the kernels' active set, after checking that it differs from the oracle's own
     only at pre-activations within the forward tolerance of zero (_check_active_set)."""
     from efgh_b200 import bilateralNN
@@ -110,6 +111,7 @@ def test_bcl_backward_every_enet_level_vs_oracle(level, sensor, dev, monkeypatch
     for dgrad_tc in (True, False):
         for idx_dtype in ((torch.int64, torch.int32) if dgrad_tc else (torch.int64,)):
             monkeypatch.setattr(bilateralNN, "DGRAD_ON_TENSOR_CORES", dgrad_tc)
+            monkeypatch.setattr(bilateralNN, "WGRAD_ON_TENSOR_CORES", dgrad_tc)    # (the scatter pass also takes the fp32 CUDA-core weight gradient)
             m.zero_grad(set_to_none=True)
             feat = feat0.to(dev).requires_grad_(True)
             off = d["pc1_lattice_offset"].to(idx_dtype)

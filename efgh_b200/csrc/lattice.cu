@@ -536,18 +536,6 @@ k_assign(efgh_lattice_state *st, const int4 *__restrict__ slots, Entry *table,
     }
 }
 
-__device__ __forceinline__ int table_find(const Entry *__restrict__ table, unsigned mask, unsigned long long key) {
-  unsigned h = hash_key(key) & mask;
-  for (unsigned probes = 0; probes <= mask; ++probes) {
-    const int4 e = *reinterpret_cast<const int4 *>(table + h);         // key + index in one 16-byte load
-    const unsigned long long cur = ((unsigned long long)(unsigned)e.y << 32) | (unsigned)e.x;
-    if (cur == key) return e.w;
-    if (cur == kEmpty) return -1;
-    h = (h + 1) & mask;
-  }
-  return -1;
-}
-
 #ifndef EFGH_LB_VERTICES
 #define EFGH_LB_VERTICES 4
 #endif

@@ -90,17 +90,6 @@ __device__ __forceinline__ void w_commit(uint32_t bar) {
       "}" ::"r"(bar)
       : "memory");
 }
-// both operands from shared memory; the whole (converged) warp executes, one elected lane issues
-__device__ __forceinline__ void w_umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
-}
 // One stage (32 vertices = 4 k-steps of 1024 bytes) under ONE election, descriptors advanced inside the block:
 //   A_raw x [G_raw | G_small] -> d (N' = 2 Np: main | correction),  A_small x G_raw -> d_corr (N = Np),
 // then the commit that frees the stage.  tools/umma_chain_probe.cu: an MMA issued from a block like this costs 15 / 18 / 36 /

@@ -12,7 +12,10 @@ st = torch.cuda.current_stream().cuda_stream
 scans = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 FLAGS = [int(v, 0) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0]
 NS = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [3]
-for (H, C, F, M) in [(100654, 36, 15, 32), (62551, 36, 15, 64), (23050, 68, 15, 128), (4194, 132, 15, 256), (885, 260, 15, 256), (100654, 32, 1, 32)]:
+SHAPES = [(100654, 36, 15, 32), (62551, 36, 15, 64), (23050, 68, 15, 128), (4194, 132, 15, 256), (885, 260, 15, 256), (100654, 32, 1, 32)]
+if len(sys.argv) > 4:      # extra shapes: "H,C,F,M;H,C,F,M" (e.g. the aligned-row variants 32 / 64 channels of levels 0-2)
+    SHAPES = [tuple(int(v) for v in t.split(',')) for t in sys.argv[4].split(';')]
+for (H, C, F, M) in SHAPES:
     H *= scans
     X = torch.randn(H + 1, C, device=dev); X[0] = 0
     nbr = torch.randint(-1, H, (F, H), device=dev, dtype=torch.int32) if F > 1 else None
